@@ -1,0 +1,934 @@
+// gxsv.cu — host side of the gxsv engine and its C ABI (include/gxsv.h).
+//
+// Holds the private physical layout (which physical bit carries which logical
+// qubit, which bits are dead), the pending real/complex normalisation, the
+// queue of un-issued CZs, and launches the kernels of kernels.cuh.
+//
+// Reference semantics reproduced (TeamGraphix/graphix):
+//   graphix/sim/statevec.py:52-750   class Statevector
+//   graphix/sim/statevec.py:841-1198 numba kernels
+#include "../../include/gxsv.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+using namespace gxk;
+typedef std::complex<double> cplx;
+
+namespace {
+
+constexpr int HOLE_MIN = 8;     // dead bits are only ever created at physical bit >= HOLE_MIN
+constexpr int TILE_BITS = 11;   // k_contract<4,true>: a CTA tile spans the lowest 11 live bits
+constexpr int U_DEF = 4;
+constexpr int RING = 256;
+constexpr int MAX_GRID = 148 * 8;
+constexpr int GXSV_VERSION = 100;
+
+struct Qubit {
+  int phys;     // physical bit, -1 while virtual (lazy mode)
+  cplx s0, s1;  // single-qubit state while virtual
+};
+
+struct ProfRec {
+  int kind;
+  cudaEvent_t e0, e1;
+};
+
+}  // namespace
+
+struct gxsv {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double2* psi = nullptr;
+  bool own_buf = true;
+  int cap_bits = 0;
+  int phys_bits = 0;       // all live physical bits are < phys_bits
+  uint64_t live_mask = 0;  // set bits = physical bits carrying a materialised qubit
+  std::vector<Qubit> q;    // logical order (reference order: index 0 = MSB)
+  std::vector<std::pair<int, int>> pend;  // queued CZs as (physical bit, physical bit)
+  cplx hscale = 1.0;       // host part of the pending scalar: true psi = g(device) * hscale * stored
+  // device control + result ring
+  Ctrl* ctrl = nullptr;
+  double* partials = nullptr;
+  Res* ring_host = nullptr;
+  Res* ring_dev = nullptr;
+  unsigned long long seq = 0;
+  GatherTables* tabs_dev = nullptr;
+  double2* stage[2] = {nullptr, nullptr};
+  size_t stage_amps = 0;
+  // options
+  int fusion = 1;
+  int strict = 1;
+  int profile = 0;
+  int sm_count = 148;
+  gxsv_stats_t stats;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  std::string err;
+};
+
+static thread_local std::string g_err;
+
+namespace {
+
+int fail(gxsv_t* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? GXSV_ENOMEM : GXSV_ECUDA, "%s: %s", #call, \
+                  cudaGetErrorString(e_));                                                         \
+  } while (0)
+
+inline double2 d2(cplx z) { return make_double2(z.real(), z.imag()); }
+
+// sorted list of dead bits below phys_bits, plus up to two extra (axis) bits
+Holes make_holes(const gxsv_t* h, int extra0 = -1, int extra1 = -1) {
+  Holes r;
+  r.n = 0;
+  for (int b = 0; b < h->phys_bits; ++b) {
+    const bool dead = !((h->live_mask >> b) & 1ull);
+    if (dead || b == extra0 || b == extra1) r.pos[r.n++] = (unsigned char)b;
+  }
+  // an extra bit at/above phys_bits needs no insertion (rank indices have no bits there)
+  return r;
+}
+
+Holes holes_of_mask(uint64_t live, int extent, int extra0 = -1) {
+  Holes r;
+  r.n = 0;
+  for (int b = 0; b < extent; ++b) {
+    const bool dead = !((live >> b) & 1ull);
+    if (dead || b == extra0) r.pos[r.n++] = (unsigned char)b;
+  }
+  return r;
+}
+
+int nlive_bits(const gxsv_t* h) { return __builtin_popcountll(h->live_mask); }
+
+int grid_for(const gxsv_t* h, uint64_t work, int per_thread) {
+  const uint64_t chunk = (uint64_t)TPB * per_thread;
+  uint64_t blocks = (work + chunk - 1) / chunk;
+  const uint64_t cap = (uint64_t)h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// --- profiling brackets ---------------------------------------------------
+cudaEvent_t get_event(gxsv_t* h) {
+  if (!h->ev_pool.empty()) {
+    cudaEvent_t e = h->ev_pool.back();
+    h->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct Launch {
+  gxsv_t* h;
+  int kind;
+  cudaEvent_t e0 = nullptr;
+  Launch(gxsv_t* h_, int kind_, double bytes) : h(h_), kind(kind_) {
+    h->stats.launches[kind] += 1;
+    h->stats.algo_bytes[kind] += bytes;
+    if (h->profile) {
+      e0 = get_event(h);
+      cudaEventRecord(e0, h->stream);
+    }
+  }
+  ~Launch() {
+    if (h->profile) {
+      cudaEvent_t e1 = get_event(h);
+      cudaEventRecord(e1, h->stream);
+      h->prof.push_back({kind, e0, e1});
+    }
+  }
+};
+
+void prof_collect(gxsv_t* h) {
+  if (h->prof.empty()) return;
+  cudaStreamSynchronize(h->stream);
+  for (auto& r : h->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) h->stats.device_ms[r.kind] += ms;
+    h->ev_pool.push_back(r.e0);
+    h->ev_pool.push_back(r.e1);
+  }
+  h->prof.clear();
+}
+
+// --- result ring ------------------------------------------------------------
+Res* next_slot(gxsv_t* h, unsigned long long* seq_out) {
+  h->seq += 1;
+  *seq_out = h->seq;
+  return h->ring_dev + (h->seq % RING);
+}
+
+int wait_slot(gxsv_t* h, unsigned long long seq, double out[4]) {
+  volatile Res* r = h->ring_host + (seq % RING);
+  unsigned long spins = 0;
+  while (r->seq != seq) {
+    if ((++spins & 0x3fff) == 0) {
+      cudaError_t e = cudaStreamQuery(h->stream);
+      if (e == cudaSuccess) {
+        if (r->seq == seq) break;
+        // kernel finished without publishing: should not happen
+        if (spins > (1ul << 26)) return fail(h, GXSV_ECUDA, "result slot %llu never published", seq);
+      } else if (e != cudaErrorNotReady) {
+        return fail(h, GXSV_ECUDA, "device error while waiting: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  __sync_synchronize();
+  for (int i = 0; i < 4; ++i) out[i] = r->v[i];
+  return GXSV_OK;
+}
+
+int check_launch(gxsv_t* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, GXSV_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return GXSV_OK;
+}
+
+void trim_extent(gxsv_t* h) {
+  while (h->phys_bits > 0 && !((h->live_mask >> (h->phys_bits - 1)) & 1ull)) h->phys_bits -= 1;
+}
+
+int check_q(gxsv_t* h, int q) {
+  if (q < 0 || q >= (int)h->q.size())
+    return fail(h, GXSV_EINDEX, "Qubit index %d out of range [0, %d]", q, (int)h->q.size() - 1);
+  return GXSV_OK;
+}
+
+double state_bytes(const gxsv_t* h) { return 16.0 * std::ldexp(1.0, nlive_bits(h)); }
+
+// --- E-run flush ------------------------------------------------------------
+int flush_pending(gxsv_t* h) {
+  if (h->pend.empty()) return GXSV_OK;
+  // CZ^2 = 1: cancel duplicates
+  std::vector<std::pair<int, int>> edges;
+  for (auto e : h->pend) {
+    if (e.first > e.second) std::swap(e.first, e.second);
+    auto it = std::find(edges.begin(), edges.end(), e);
+    if (it != edges.end()) edges.erase(it); else edges.push_back(e);
+  }
+  h->pend.clear();
+  const int n = nlive_bits(h);
+  const double S = state_bytes(h);
+  while (!edges.empty()) {
+    // vertex of highest degree becomes the pivot of a star
+    int deg[64] = {0};
+    for (auto& e : edges) { deg[e.first]++; deg[e.second]++; }
+    int m = 0;
+    for (int b = 1; b < 64; ++b) if (deg[b] > deg[m]) m = b;
+    const bool single_star = (deg[m] == (int)edges.size());
+    if (!single_star && edges.size() <= 64 && edges.size() > 2) {
+      // several stars: one general diagonal pass over the whole state is cheaper than >= 3 star passes
+      EdgeList el;
+      el.n = (int)edges.size();
+      for (int i = 0; i < el.n; ++i) { el.a[i] = (unsigned char)edges[i].first; el.b[i] = (unsigned char)edges[i].second; }
+      const uint64_t nlive = 1ull << n;
+      Holes hs = make_holes(h);
+      {
+        Launch L(h, GXSV_K_CZ, 1.5 * S);
+        k_diag_edges<U_DEF><<<grid_for(h, nlive, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, el, 0ull, nlive);
+      }
+      edges.clear();
+      return check_launch(h, "k_diag_edges");
+    }
+    uint64_t nbr = 0;
+    std::vector<std::pair<int, int>> rest;
+    for (auto& e : edges) {
+      if (e.first == m) nbr |= 1ull << e.second;
+      else if (e.second == m) nbr |= 1ull << e.first;
+      else rest.push_back(e);
+    }
+    edges.swap(rest);
+    const int hb = 63 - __builtin_clzll(nbr);
+    const uint64_t nbr_rest = nbr & ~(1ull << hb);
+    const uint64_t nquarter = (n >= 2) ? (1ull << (n - 2)) : 0;
+    if (nquarter == 0) continue;
+    Holes hs = make_holes(h, m, hb);
+    // algorithmic bytes: the flipped quarter read + written; a participating bit below
+    // the 32-byte sector (bit 0) forces whole sectors of the pivot half to move
+    int lowbit = std::min(m, __builtin_ctzll(nbr));
+    const double bytes = (lowbit == 0) ? S : 0.5 * S;
+    {
+      Launch L(h, GXSV_K_CZ, bytes);
+      k_cz_star<U_DEF><<<grid_for(h, nquarter, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, m, hb, nbr_rest, nquarter);
+    }
+    int rc = check_launch(h, "k_cz_star");
+    if (rc) return rc;
+  }
+  return GXSV_OK;
+}
+
+// choose the physical bit for a new qubit: lowest hole, else the next bit on top
+int alloc_bit(gxsv_t* h, int* bit) {
+  for (int b = 0; b < h->phys_bits; ++b)
+    if (!((h->live_mask >> b) & 1ull)) { *bit = b; return GXSV_OK; }
+  if (h->phys_bits + 1 > h->cap_bits) {
+    int rc = gxsv_ensure_capacity(h, h->phys_bits + 1);
+    if (rc) return rc;
+  }
+  *bit = h->phys_bits;
+  return GXSV_OK;
+}
+
+int add_one(gxsv_t* h, cplx s0, cplx s1) {
+  int rc = flush_pending(h);
+  if (rc) return rc;
+  int hb;
+  rc = alloc_bit(h, &hb);
+  if (rc) return rc;
+  const int n = nlive_bits(h);
+  const uint64_t nlive = 1ull << n;
+  const double S = 16.0 * (double)nlive;
+  Holes hs = make_holes(h, hb);
+  const int grid = grid_for(h, nlive, U_DEF);
+  const double a0 = std::abs(s0), a1 = std::abs(s1);
+  if (a0 >= a1 || a0 > 0.25) {
+    // defer s0 to the host scalar; upper half = (s1/s0) * lower half
+    const cplx f1 = s1 / s0;
+    Launch L(h, GXSV_K_FILL, 2.0 * S);
+    if (f1 == cplx(1.0, 0.0))
+      k_fill<U_DEF, 0><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hb, d2(1.0), d2(1.0), nlive);
+    else
+      k_fill<U_DEF, 1><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hb, d2(1.0), d2(f1), nlive);
+    h->hscale *= s0;
+  } else {
+    // |s0| small (e.g. |1>): defer s1 instead, lower half scaled by s0/s1
+    const cplx f0 = s0 / s1;
+    Launch L(h, GXSV_K_FILL, 3.0 * S);
+    k_fill<U_DEF, 2><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hb, d2(f0), d2(1.0), nlive);
+    h->hscale *= s1;
+  }
+  rc = check_launch(h, "k_fill");
+  if (rc) return rc;
+  h->live_mask |= 1ull << hb;
+  if (hb >= h->phys_bits) h->phys_bits = hb + 1;
+  h->q.push_back({hb, 0.0, 0.0});
+  return GXSV_OK;
+}
+
+// Launch the contraction of physical bit p with bra (c0, c1) (host scalar already folded in by
+// the caller) and update the layout.  `qidx` = logical index of the measured qubit.
+int launch_contract(gxsv_t* h, int qidx, cplx c0, cplx c1, unsigned long long* seq_out) {
+  const int p = h->q[qidx].phys;
+  const int n = nlive_bits(h);
+  const uint64_t nout = 1ull << (n - 1);
+  const double S = state_bytes(h);
+  std::vector<int> L;  // live physical bits, ascending
+  for (int b = 0; b < h->phys_bits; ++b) if ((h->live_mask >> b) & 1ull) L.push_back(b);
+  const bool tile = (n <= TILE_BITS) || (p < HOLE_MIN);
+  unsigned long long seq;
+  Res* slot = next_slot(h, &seq);
+  *seq_out = seq;
+  Holes hs = make_holes(h, p);
+  if (!tile) {
+    const int grid = grid_for(h, nout, U_DEF);
+    {
+      Launch Lc(h, GXSV_K_CONTRACT, 1.5 * S);
+      k_contract<U_DEF, false><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hs, p, d2(c0), d2(c1), nout, h->partials,
+                                                           h->ctrl, slot, seq);
+    }
+    h->live_mask &= ~(1ull << p);
+  } else {
+    const int K = std::min(TILE_BITS, n);
+    const int top = L[K - 1];  // the tile's top live bit becomes the hole
+    int t = 0;
+    while (L[t] != p) ++t;
+    const uint64_t live_after = h->live_mask & ~(1ull << top);
+    Holes hd = holes_of_mask(live_after, h->phys_bits);
+    // every CTA must own whole tiles: grid = number of 1024-output chunks (capped, grid-stride keeps alignment)
+    const int grid = grid_for(h, nout, U_DEF);
+    {
+      Launch Lc(h, GXSV_K_CONTRACT, 1.5 * S);
+      k_contract<U_DEF, true><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hd, p, d2(c0), d2(c1), nout, h->partials,
+                                                          h->ctrl, slot, seq);
+    }
+    // qubits on L[t+1 .. K-1] slide down one live slot
+    for (auto& qb : h->q) {
+      if (qb.phys < 0) continue;
+      for (int i = t + 1; i <= K - 1; ++i)
+        if (qb.phys == L[i]) { qb.phys = L[i - 1]; break; }
+    }
+    h->live_mask = live_after;
+  }
+  int rc = check_launch(h, "k_contract");
+  if (rc) return rc;
+  h->q.erase(h->q.begin() + qidx);
+  trim_extent(h);
+  return GXSV_OK;
+}
+
+int ensure_stage(gxsv_t* h, size_t amps) {
+  if (h->stage_amps >= amps) return GXSV_OK;
+  for (int i = 0; i < 2; ++i) if (h->stage[i]) { cudaFree(h->stage[i]); h->stage[i] = nullptr; }
+  h->stage_amps = 0;
+  for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->stage[i], amps * sizeof(double2)));
+  h->stage_amps = amps;
+  return GXSV_OK;
+}
+
+int upload_tables(gxsv_t* h) {
+  // canonical index bit (n-1-q) of logical qubit q  ->  physical bit q.phys
+  const int n = (int)h->q.size();
+  static thread_local GatherTables t;
+  for (int byte = 0; byte < 5; ++byte) {
+    for (int v = 0; v < 256; ++v) {
+      uint64_t p = 0;
+      for (int b = 0; b < 8; ++b) {
+        if (!((v >> b) & 1)) continue;
+        const int bit = byte * 8 + b;  // canonical bit index
+        if (bit >= n) continue;
+        const int ql = n - 1 - bit;
+        p |= 1ull << h->q[ql].phys;
+      }
+      t.t[byte][v] = p;
+    }
+  }
+  CU(cudaMemcpyAsync(h->tabs_dev, &t, sizeof t, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return GXSV_OK;
+}
+
+int init_common(gxsv_t* h) {
+  CU(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  CU(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
+  CU(cudaMalloc(&h->partials, sizeof(double) * 4 * (size_t)(h->sm_count * 8 + 8)));
+  CU(cudaMalloc(&h->tabs_dev, sizeof(GatherTables)));
+  CU(cudaHostAlloc(&h->ring_host, sizeof(Res) * RING, cudaHostAllocMapped));
+  memset(h->ring_host, 0, sizeof(Res) * RING);
+  CU(cudaHostGetDevicePointer((void**)&h->ring_dev, h->ring_host, 0));
+  memset(&h->stats, 0, sizeof h->stats);
+  return gxsv_reset(h);
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int gxsv_version(void) { return GXSV_VERSION; }
+
+const char* gxsv_last_error(gxsv_t* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
+  gxsv_t* h = nullptr;
+  if (!out) return fail(h, GXSV_EVALUE, "out is NULL");
+  if (max_qubits < 0 || max_qubits > 40) return fail(h, GXSV_EVALUE, "`max_qubits` must be in [0, 40], got %d", max_qubits);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(h, GXSV_ECUDA, "no CUDA device available (%s): the gxsv engine has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(h, GXSV_EVALUE, "device %d out of range [0, %d)", device, ndev);
+  h = new gxsv();
+  h->device = device;
+  h->stream = (cudaStream_t)stream;
+  h->cap_bits = max_qubits;
+  h->own_buf = true;
+  cudaSetDevice(device);
+  e = cudaMalloc(&h->psi, sizeof(double2) << max_qubits);
+  if (e != cudaSuccess) {
+    int rc = fail(nullptr, GXSV_ENOMEM, "cudaMalloc of %.3f GiB failed: %s", std::ldexp(16.0, max_qubits - 30),
+                  cudaGetErrorString(e));
+    delete h;
+    return rc;
+  }
+  int rc = init_common(h);
+  if (rc) { g_err = h->err; gxsv_destroy(h); return rc; }
+  *out = h;
+  return GXSV_OK;
+}
+
+int gxsv_create_external(void* device_buffer, int cap_qubits, int device, void* stream, gxsv_t** out) {
+  gxsv_t* h = nullptr;
+  if (!out || !device_buffer) return fail(h, GXSV_EVALUE, "NULL argument");
+  h = new gxsv();
+  h->device = device;
+  h->stream = (cudaStream_t)stream;
+  h->cap_bits = cap_qubits;
+  h->own_buf = false;
+  h->psi = (double2*)device_buffer;
+  int rc = init_common(h);
+  if (rc) { g_err = h->err; gxsv_destroy(h); return rc; }
+  *out = h;
+  return GXSV_OK;
+}
+
+int gxsv_destroy(gxsv_t* h) {
+  if (!h) return GXSV_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  prof_collect(h);
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->own_buf && h->psi) cudaFree(h->psi);
+  if (h->ctrl) cudaFree(h->ctrl);
+  if (h->partials) cudaFree(h->partials);
+  if (h->tabs_dev) cudaFree(h->tabs_dev);
+  if (h->ring_host) cudaFreeHost(h->ring_host);
+  for (int i = 0; i < 2; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
+  delete h;
+  return GXSV_OK;
+}
+
+int gxsv_reset(gxsv_t* h) {
+  CU(cudaSetDevice(h->device));
+  h->q.clear();
+  h->pend.clear();
+  h->phys_bits = 0;
+  h->live_mask = 0;
+  h->hscale = 1.0;
+  const double2 one = make_double2(1.0, 0.0);
+  const Ctrl c0 = {1.0, 0u, 0u};
+  CU(cudaMemcpyAsync(h->psi, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->ctrl, &c0, sizeof c0, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return GXSV_OK;
+}
+
+int gxsv_set_option(gxsv_t* h, int key, int value) {
+  switch (key) {
+    case GXSV_OPT_FUSION:
+      if (value < 0 || value > 2) return fail(h, GXSV_EVALUE, "fusion must be 0, 1 or 2");
+      { int rc = gxsv_flush(h); if (rc) return rc; }
+      h->fusion = value;
+      return GXSV_OK;
+    case GXSV_OPT_STRICT: h->strict = value ? 1 : 0; return GXSV_OK;
+    case GXSV_OPT_PROFILE:
+      if (!value) prof_collect(h);
+      h->profile = value ? 1 : 0;
+      return GXSV_OK;
+    default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
+  }
+}
+
+int gxsv_get_option(gxsv_t* h, int key, int* value) {
+  switch (key) {
+    case GXSV_OPT_FUSION: *value = h->fusion; return GXSV_OK;
+    case GXSV_OPT_STRICT: *value = h->strict; return GXSV_OK;
+    case GXSV_OPT_PROFILE: *value = h->profile; return GXSV_OK;
+    default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
+  }
+}
+
+int gxsv_nqubit(gxsv_t* h) { return (int)h->q.size(); }
+int gxsv_max_qubits(gxsv_t* h) { return h->cap_bits; }
+
+int gxsv_ensure_capacity(gxsv_t* h, int required_qubits) {
+  if (required_qubits <= h->cap_bits) return GXSV_OK;
+  if (required_qubits > 40) return fail(h, GXSV_EVALUE, "capacity of %d qubits exceeds the 40-qubit index space", required_qubits);
+  if (!h->own_buf) return fail(h, GXSV_ENOMEM, "external buffer of 2^%d amplitudes cannot grow to 2^%d", h->cap_bits, required_qubits);
+  CU(cudaSetDevice(h->device));
+  double2* nb = nullptr;
+  CU(cudaMalloc(&nb, sizeof(double2) << required_qubits));
+  CU(cudaMemcpyAsync(nb, h->psi, sizeof(double2) << h->phys_bits, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(h->psi));
+  h->psi = nb;
+  h->cap_bits = required_qubits;
+  return GXSV_OK;
+}
+
+int gxsv_add_plus(gxsv_t* h) {
+  CU(cudaSetDevice(h->device));
+  const double r = 1.0 / std::sqrt(2.0);
+  return add_one(h, cplx(r, 0.0), cplx(r, 0.0));
+}
+
+int gxsv_add_qubit(gxsv_t* h, const double amp[4]) {
+  CU(cudaSetDevice(h->device));
+  const cplx s0(amp[0], amp[1]), s1(amp[2], amp[3]);
+  if (std::abs(s0) == 0.0 && std::abs(s1) == 0.0) return fail(h, GXSV_EVALUE, "zero single-qubit state");
+  return add_one(h, s0, s1);
+}
+
+int gxsv_tensor(gxsv_t* h, int k, const double* vec) {
+  CU(cudaSetDevice(h->device));
+  if (k < 0 || k > 30) return fail(h, GXSV_EVALUE, "tensor: k = %d out of range", k);
+  if (k == 0) { h->hscale *= cplx(vec[0], vec[1]); return GXSV_OK; }
+  int rc = flush_pending(h);
+  if (rc) return rc;
+  const int n = nlive_bits(h);
+  const uint64_t nnew = 1ull << k;
+  if (n == 0) {
+    // empty register: upload in canonical order (new qubit j <-> physical bit k-1-j), psi[0] (the scalar) folded in
+    rc = gxsv_ensure_capacity(h, k);
+    if (rc) return rc;
+    // the 0-qubit state is the scalar g*hscale*psi[0]; keep it (phase included) in hscale
+    double2 s0;
+    Ctrl c;
+    CU(cudaMemcpyAsync(&s0, h->psi, sizeof s0, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&c, h->ctrl, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->hscale *= cplx(s0.x, s0.y) * c.g;
+    c.g = 1.0;
+    c.ticket = 0;
+    CU(cudaMemcpyAsync(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->psi, vec, sizeof(double2) * nnew, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->stats.launches[GXSV_K_TENSOR] += 1;
+    h->stats.algo_bytes[GXSV_K_TENSOR] += 16.0 * (double)nnew;
+    h->phys_bits = k;
+    h->live_mask = nnew - 1ull;
+    for (int j = 0; j < k; ++j) h->q.push_back({k - 1 - j, 0.0, 0.0});
+    // the previous scalar psi[0]*g*hscale keeps living in hscale/g (psi[0] was 1 by construction after reset/M)
+    return GXSV_OK;
+  }
+  NewBits nb;
+  nb.k = k;
+  uint64_t mask = h->live_mask;
+  int extent = h->phys_bits;
+  for (int j = 0; j < k; ++j) {
+    int bit = -1;
+    for (int b = 0; b < extent; ++b) if (!((mask >> b) & 1ull)) { bit = b; break; }
+    if (bit < 0) bit = extent;
+    if (bit >= extent) extent = bit + 1;
+    mask |= 1ull << bit;
+    nb.pos[j] = (unsigned char)bit;
+  }
+  if (extent > h->cap_bits) { rc = gxsv_ensure_capacity(h, extent); if (rc) return rc; }
+  double2* dvec = nullptr;
+  CU(cudaMalloc(&dvec, sizeof(double2) * nnew));
+  CU(cudaMemcpyAsync(dvec, vec, sizeof(double2) * nnew, cudaMemcpyHostToDevice, h->stream));
+  const uint64_t nlive = 1ull << n;
+  Holes hs = make_holes(h);
+  {
+    Launch L(h, GXSV_K_TENSOR, 16.0 * (double)nlive * (double)(nnew + 1));
+    k_tensor<<<grid_for(h, nlive << k, 1), TPB, 0, h->stream>>>(h->psi, hs, nb, dvec, nlive, n);
+    k_scale_all<U_DEF><<<grid_for(h, nlive, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, make_double2(vec[0], vec[1]), nlive);
+  }
+  rc = check_launch(h, "k_tensor");
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(dvec));
+  if (rc) return rc;
+  h->live_mask = mask;
+  h->phys_bits = extent;
+  for (int j = 0; j < k; ++j) h->q.push_back({(int)nb.pos[j], 0.0, 0.0});
+  return GXSV_OK;
+}
+
+int gxsv_set_state(gxsv_t* h, int n, const double* vec_host) {
+  int rc = gxsv_reset(h);
+  if (rc) return rc;
+  return gxsv_tensor(h, n, vec_host);
+}
+
+int gxsv_entangle(gxsv_t* h, int q1, int q2) {
+  int rc = check_q(h, q1);
+  if (rc) return rc;
+  rc = check_q(h, q2);
+  if (rc) return rc;
+  if (q1 == q2) return fail(h, GXSV_EVALUE, "entangle: control and target must differ");
+  h->pend.push_back({h->q[q1].phys, h->q[q2].phys});
+  if (h->fusion == 0) { CU(cudaSetDevice(h->device)); return flush_pending(h); }
+  return GXSV_OK;
+}
+
+int gxsv_flush(gxsv_t* h) {
+  CU(cudaSetDevice(h->device));
+  return flush_pending(h);
+}
+
+int gxsv_evolve_single(gxsv_t* h, int q, const double m[8]) {
+  CU(cudaSetDevice(h->device));
+  int rc = check_q(h, q);
+  if (rc) return rc;
+  rc = flush_pending(h);
+  if (rc) return rc;
+  const cplx m00(m[0], m[1]), m01(m[2], m[3]), m10(m[4], m[5]), m11(m[6], m[7]);
+  const int p = h->q[q].phys;
+  const int n = nlive_bits(h);
+  const uint64_t npair = 1ull << (n - 1);
+  const double S = state_bytes(h);
+  Holes hs = make_holes(h, p);
+  const int grid = grid_for(h, npair, U_DEF);
+  if (m01 == cplx(0.0) && m10 == cplx(0.0) && std::abs(m00) > 0.0) {
+    // diagonal: fold m00 into the host scalar, scale only the bit = 1 half
+    const cplx f = m11 / m00;
+    h->hscale *= m00;
+    if (f == cplx(1.0, 0.0)) return GXSV_OK;
+    Launch L(h, GXSV_K_APPLY1Q, (p == 0) ? 2.0 * S : S);
+    k_scale_half<U_DEF><<<grid, TPB, 0, h->stream>>>(h->psi, hs, p, d2(f), npair);
+  } else {
+    Launch L(h, GXSV_K_APPLY1Q, 2.0 * S);
+    k_apply1q<U_DEF><<<grid, TPB, 0, h->stream>>>(h->psi, hs, p, d2(m00), d2(m01), d2(m10), d2(m11), npair);
+  }
+  return check_launch(h, "k_apply1q");
+}
+
+int gxsv_swap(gxsv_t* h, int q1, int q2) {
+  int rc = check_q(h, q1);
+  if (rc) return rc;
+  rc = check_q(h, q2);
+  if (rc) return rc;
+  // a relabel: the amplitudes do not move (pending CZs are stored by physical bit, so they stay valid)
+  std::swap(h->q[q1], h->q[q2]);
+  // but queued CZs refer to physical bits of the *qubits*, which just traded places logically, not physically: nothing to fix
+  return GXSV_OK;
+}
+
+int gxsv_evolve(gxsv_t* h, int k, const int* qubits, const double* op) {
+  (void)k; (void)qubits; (void)op;
+  return fail(h, GXSV_EUNSUPPORTED, "k-qubit evolve is not part of the pattern path (statevec.py:375-377)");
+}
+
+int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) {
+  CU(cudaSetDevice(h->device));
+  int rc = check_q(h, q);
+  if (rc) return rc;
+  rc = flush_pending(h);
+  if (rc) return rc;
+  const int p = h->q[q].phys;
+  const int n = nlive_bits(h);
+  const uint64_t npair = 1ull << (n - 1);
+  Holes hs = make_holes(h, p);
+  unsigned long long seq;
+  Res* slot = next_slot(h, &seq);
+  {
+    Launch L(h, GXSV_K_EXPECT, state_bytes(h));
+    k_pair_reduce<U_DEF, 0><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(
+        h->psi, hs, p, make_double2(m[0], m[1]), make_double2(m[2], m[3]), make_double2(m[4], m[5]),
+        make_double2(m[6], m[7]), npair, h->partials, h->ctrl, slot, seq, std::norm(h->hscale));
+  }
+  rc = check_launch(h, "k_pair_reduce");
+  if (rc) return rc;
+  double v[4];
+  rc = wait_slot(h, seq, v);
+  if (rc) return rc;
+  out[0] = v[0];
+  out[1] = v[1];
+  return GXSV_OK;
+}
+
+int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double norms[2]) {
+  CU(cudaSetDevice(h->device));
+  int rc = check_q(h, q);
+  if (rc) return rc;
+  rc = flush_pending(h);
+  if (rc) return rc;
+  const cplx m00(m[0], m[1]), m01(m[2], m[3]), m10(m[4], m[5]), m11(m[6], m[7]);
+  const double r0 = std::norm(m00) + std::norm(m01), r1 = std::norm(m10) + std::norm(m11);
+  if (r0 + r1 == 0.0) return fail(h, GXSV_EZERONORM, "Attempted to remove qubit %d from 0-norm statevector.", q);
+  const double det = std::abs(m00 * m11 - m01 * m10);
+  const bool rank1 = det <= 1e-13 * (r0 + r1);
+  const int p = h->q[q].phys;
+  const int n = nlive_bits(h);
+  double v[4];
+  unsigned long long seq;
+  if (rank1) {
+    // op = u w^T: row r = u_r * w.  Contract with the larger row (best conditioned); the two half-norms the
+    // reference computes (statevec.py:1185) differ from it only by the known factor |u_r|^2/|u_big|^2.
+    const int big = (r0 >= r1) ? 0 : 1;
+    const cplx c0 = big ? m10 : m00, c1 = big ? m11 : m01;
+    const double rbig = big ? r1 : r0;
+    rc = launch_contract(h, q, c0 * h->hscale, c1 * h->hscale, &seq);
+    if (rc) return rc;
+    h->hscale = 1.0;
+    if (!h->strict) {
+      if (norms) { norms[0] = norms[1] = NAN; }
+      return GXSV_OK;
+    }
+    rc = wait_slot(h, seq, v);
+    if (rc) return rc;
+    const double nbig = v[0];
+    const double n0 = nbig * (r0 / rbig), n1 = nbig * (r1 / rbig);
+    if (norms) { norms[0] = n0; norms[1] = n1; }
+    int pick = 0;
+    if (n0 <= atol) {
+      pick = 1;
+      if (n1 <= atol) return fail(h, GXSV_EZERONORM, "Attempted to remove qubit %d from 0-norm statevector.", q);
+    }
+    if (pick != big) {
+      // the reference keeps half `pick`: same vector up to the unit phase u_pick/u_big
+      const cplx ub = big ? (std::abs(m10) >= std::abs(m11) ? m10 : m11) : (std::abs(m00) >= std::abs(m01) ? m00 : m01);
+      const cplx up = big ? (std::abs(m10) >= std::abs(m11) ? m00 : m01) : (std::abs(m00) >= std::abs(m01) ? m10 : m11);
+      const cplx ratio = up / ub;
+      if (std::abs(ratio) > 0.0) h->hscale *= ratio / std::abs(ratio);
+    }
+    return GXSV_OK;
+  }
+  // general 2x2 (not a projector): literal two-pass reference algorithm
+  const uint64_t npair = 1ull << (n - 1);
+  Holes hs = make_holes(h, p);
+  Res* slot = next_slot(h, &seq);
+  {
+    Launch L(h, GXSV_K_EXPECT, state_bytes(h));
+    k_pair_reduce<U_DEF, 1><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(
+        h->psi, hs, p, d2(m00), d2(m01), d2(m10), d2(m11), npair, h->partials, h->ctrl, slot, seq,
+        std::norm(h->hscale));
+  }
+  rc = check_launch(h, "k_pair_reduce");
+  if (rc) return rc;
+  rc = wait_slot(h, seq, v);
+  if (rc) return rc;
+  if (norms) { norms[0] = v[0]; norms[1] = v[1]; }
+  int pick = 0;
+  if (v[0] <= atol) {
+    pick = 1;
+    if (v[1] <= atol) return fail(h, GXSV_EZERONORM, "Attempted to remove qubit %d from 0-norm statevector.", q);
+  }
+  rc = launch_contract(h, q, (pick ? m10 : m00) * h->hscale, (pick ? m11 : m01) * h->hscale, &seq);
+  if (rc) return rc;
+  h->hscale = 1.0;
+  if (h->strict) rc = wait_slot(h, seq, v);
+  return rc;
+}
+
+int gxsv_permute(gxsv_t* h, const int* perm, int n) {
+  if (n != (int)h->q.size()) return fail(h, GXSV_EVALUE, "Permutation has length %d, but %d qubits expected.", n, (int)h->q.size());
+  std::vector<char> seen(n, 0);
+  for (int i = 0; i < n; ++i) {
+    if (perm[i] < 0 || perm[i] >= n || seen[perm[i]]) return fail(h, GXSV_EVALUE, "not a permutation");
+    seen[perm[i]] = 1;
+  }
+  std::vector<Qubit> nq(n);
+  for (int i = 0; i < n; ++i) nq[i] = h->q[perm[i]];
+  h->q.swap(nq);
+  return GXSV_OK;
+}
+
+static int gather_chunk(gxsv_t* h, double2* out, uint64_t first, uint64_t count) {
+  Launch L(h, GXSV_K_GATHER, 32.0 * (double)count);
+  k_gather<<<grid_for(h, count, 4), TPB, 0, h->stream>>>(h->psi, out, h->tabs_dev, first, count, d2(h->hscale), h->ctrl);
+  return GXSV_OK;
+}
+
+int gxsv_flatten_device(gxsv_t* h, void* out_device) {
+  CU(cudaSetDevice(h->device));
+  int rc = flush_pending(h);
+  if (rc) return rc;
+  rc = upload_tables(h);
+  if (rc) return rc;
+  const uint64_t total = 1ull << h->q.size();
+  gather_chunk(h, (double2*)out_device, 0, total);
+  return check_launch(h, "k_gather");
+}
+
+int gxsv_flatten(gxsv_t* h, double* out_host) {
+  CU(cudaSetDevice(h->device));
+  int rc = flush_pending(h);
+  if (rc) return rc;
+  rc = upload_tables(h);
+  if (rc) return rc;
+  const uint64_t total = 1ull << h->q.size();
+  const uint64_t chunk = std::min<uint64_t>(total, 1ull << 22);
+  rc = ensure_stage(h, chunk);
+  if (rc) return rc;
+  double2* out = (double2*)out_host;
+  int buf = 0;
+  for (uint64_t first = 0; first < total; first += chunk, buf ^= 1) {
+    gather_chunk(h, h->stage[buf], first, chunk);
+    rc = check_launch(h, "k_gather");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out + first, h->stage[buf], sizeof(double2) * chunk, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return GXSV_OK;
+}
+
+int gxsv_norm2(gxsv_t* h, double* out) {
+  CU(cudaSetDevice(h->device));
+  int rc = flush_pending(h);
+  if (rc) return rc;
+  const uint64_t nlive = 1ull << nlive_bits(h);
+  Holes hs = make_holes(h);
+  unsigned long long seq;
+  Res* slot = next_slot(h, &seq);
+  {
+    Launch L(h, GXSV_K_EXPECT, state_bytes(h));
+    k_norm2<U_DEF><<<grid_for(h, nlive, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, nlive, h->partials, h->ctrl, slot, seq,
+                                                                    std::norm(h->hscale));
+  }
+  rc = check_launch(h, "k_norm2");
+  if (rc) return rc;
+  double v[4];
+  rc = wait_slot(h, seq, v);
+  if (rc) return rc;
+  *out = v[0];
+  return GXSV_OK;
+}
+
+int gxsv_fidelity(gxsv_t* a, gxsv_t* b, double* out) {
+  gxsv_t* h = a;
+  if (a->q.size() != b->q.size()) return fail(h, GXSV_EVALUE, "fidelity: qubit counts differ (%d vs %d)", (int)a->q.size(), (int)b->q.size());
+  if (a->device != b->device) return fail(h, GXSV_EVALUE, "fidelity: states live on different devices");
+  CU(cudaSetDevice(a->device));
+  const uint64_t total = 1ull << a->q.size();
+  double2 *xa = nullptr, *xb = nullptr;
+  CU(cudaMalloc(&xa, sizeof(double2) * total));
+  cudaError_t e = cudaMalloc(&xb, sizeof(double2) * total);
+  if (e != cudaSuccess) { cudaFree(xa); return fail(h, GXSV_ENOMEM, "fidelity: no room for canonical copies"); }
+  int rc = gxsv_flatten_device(a, xa);
+  if (!rc) rc = gxsv_flatten_device(b, xb);
+  if (!rc) {
+    cudaStreamSynchronize(b->stream);
+    unsigned long long seq;
+    Res* slot = next_slot(a, &seq);
+    {
+      Launch L(a, GXSV_K_EXPECT, 32.0 * (double)total);
+      k_inner<U_DEF><<<grid_for(a, total, U_DEF), TPB, 0, a->stream>>>(xa, xb, total, a->partials, a->ctrl, slot, seq);
+    }
+    rc = check_launch(a, "k_inner");
+    double v[4];
+    if (!rc) rc = wait_slot(a, seq, v);
+    if (!rc) *out = v[0] * v[0] + v[1] * v[1];
+  }
+  cudaStreamSynchronize(a->stream);
+  cudaFree(xa);
+  cudaFree(xb);
+  return rc;
+}
+
+int gxsv_sync(gxsv_t* h) {
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return GXSV_OK;
+}
+
+int gxsv_stats(gxsv_t* h, gxsv_stats_t* out) {
+  prof_collect(h);
+  *out = h->stats;
+  return GXSV_OK;
+}
+
+int gxsv_reset_stats(gxsv_t* h) {
+  prof_collect(h);
+  memset(&h->stats, 0, sizeof h->stats);
+  return GXSV_OK;
+}
+
+int gxsv_layout(gxsv_t* h, int* out) {
+  for (size_t i = 0; i < h->q.size(); ++i) out[i] = h->q[i].phys;
+  return GXSV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+/*
+ * gxsv.h — C ABI of the B200-native complex128 statevector engine that sits
+ * under graphix_b200.B200StatevectorBackend.
+ *
+ * The reference (TeamGraphix/graphix) has no FFI: its statevector path is a
+ * Python class (`graphix/sim/statevec.py:52-750`, class Statevector) whose
+ * methods call numba kernels (`statevec.py:841-1198`).  Every entry point
+ * below replaces one of those methods; the citation on each declaration is the
+ * reference method (and numba kernel) whose semantics it reproduces.  The
+ * Python binding a graphix maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - All functions return an int status (GXSV_OK == 0).  No C++ exception ever
+ *    crosses this boundary; `gxsv_last_error` returns the message.
+ *  - Qubit indices are LOGICAL and follow the reference convention
+ *    (`statevec.py:899-900,965-969`): qubit 0 is the most significant bit of
+ *    the flattened state, newly added qubits take the last indices.  The
+ *    physical layout of the amplitudes in HBM is private to the library.
+ *  - Complex numbers are pairs of doubles (re, im); 2x2 operators are 8
+ *    doubles in row-major order (m00, m01, m10, m11).
+ *  - One host thread drives a handle at a time (the reference's Backend
+ *    contract is strictly sequential, `graphix/simulator.py:449-478`).
+ *  - Device memory, streams and events are owned by the library unless an
+ *    external buffer/stream is handed in at creation.
+ */
+#ifndef GXSV_H_
+#define GXSV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gxsv gxsv_t;
+
+/* status codes; the Python layer maps them to the reference's exception types
+ * (RuntimeError / IndexError / ValueError). */
+enum {
+  GXSV_OK = 0,
+  GXSV_EINDEX = 1,    /* qubit index out of range  -> IndexError  (statevec.py:526-542) */
+  GXSV_EVALUE = 2,    /* inconsistent arguments    -> ValueError  (statevec.py:1221-1225) */
+  GXSV_EZERONORM = 3, /* projection onto 0-norm    -> RuntimeError(statevec.py:1192-1193) */
+  GXSV_ECUDA = 4,     /* CUDA runtime failure      -> RuntimeError */
+  GXSV_ENOMEM = 5,    /* device allocation failed  -> MemoryError */
+  GXSV_EUNSUPPORTED = 6
+};
+
+/* option keys for gxsv_set_option */
+enum {
+  GXSV_OPT_FUSION = 1,  /* 0 = one kernel per command, 1 = fuse runs of E (default), 2 = lazy N/E->M fusion */
+  GXSV_OPT_STRICT = 2,  /* 1 (default) = project_qubit waits for the norm and raises like the reference */
+  GXSV_OPT_PROFILE = 3  /* 1 = bracket every launch with CUDA events (gxsv_profile_read) */
+};
+
+/* kernel kinds reported by gxsv_profile_read / gxsv_stats */
+enum {
+  GXSV_K_FILL = 0,     /* N: append one qubit (copy-fill of a free physical bit) */
+  GXSV_K_CZ = 1,       /* E-run: fused diagonal CZ phase pass */
+  GXSV_K_CONTRACT = 2, /* M: project + compact + norm reduction */
+  GXSV_K_APPLY1Q = 3,  /* X / Z / C: 2x2 on one axis */
+  GXSV_K_EXPECT = 4,   /* probability / expectation reduction */
+  GXSV_K_GATHER = 5,   /* finalize / flatten permutation gather */
+  GXSV_K_FUSED = 6,    /* lazy N,E..,M fused butterfly */
+  GXSV_K_TENSOR = 7,   /* general add_nodes (2^k vector) */
+  GXSV_K_MISC = 8,
+  GXSV_K_COUNT = 9
+};
+
+typedef struct {
+  uint64_t launches[GXSV_K_COUNT];   /* kernels launched per kind since create/reset_stats */
+  double algo_bytes[GXSV_K_COUNT];   /* algorithmic bytes of those launches */
+  double device_ms[GXSV_K_COUNT];    /* CUDA-event time per kind (only while GXSV_OPT_PROFILE = 1) */
+} gxsv_stats_t;
+
+/* ---- lifetime ------------------------------------------------------- */
+
+/* Statevector(nqubit=0, max_qubits=N)  — statevec.py:93-216, with_capacity :807-832.
+ * `stream` is a cudaStream_t (NULL = legacy default stream). */
+int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out);
+/* Same, on caller-owned device memory of 2^cap_qubits complex128 (used for sharded states). */
+int gxsv_create_external(void* device_buffer, int cap_qubits, int device, void* stream, gxsv_t** out);
+int gxsv_destroy(gxsv_t* h);
+/* back to the 0-qubit scalar state [1] */
+int gxsv_reset(gxsv_t* h);
+const char* gxsv_last_error(gxsv_t* h);
+int gxsv_set_option(gxsv_t* h, int key, int value);
+int gxsv_get_option(gxsv_t* h, int key, int* value);
+
+/* ---- queries -------------------------------------------------------- */
+
+int gxsv_nqubit(gxsv_t* h);       /* Statevector.nqubit      statevec.py:232-236 */
+int gxsv_max_qubits(gxsv_t* h);   /* Statevector.max_qubits  statevec.py:238-241 */
+/* Statevector.ensure_capacity    statevec.py:243-259 */
+int gxsv_ensure_capacity(gxsv_t* h, int required_qubits);
+
+/* ---- N: add qubits -------------------------------------------------- */
+
+/* add_nodes fast path, |+> appended as the new last qubit
+ * statevec.py:269-300 -> _add_default_node_jit :867-887 */
+int gxsv_add_plus(gxsv_t* h);
+/* one qubit in state (s0, s1) = amp[0..3]; PlanarState.to_statevector_numpy states.py:67-79 */
+int gxsv_add_qubit(gxsv_t* h, const double amp[4]);
+/* psi <- psi (x) vec, vec = 2^k complex128 in reference order
+ * Statevector.tensor statevec.py:508-524 -> _tensor_jit :841-864 */
+int gxsv_tensor(gxsv_t* h, int k, const double* vec);
+
+/* ---- E: CZ ---------------------------------------------------------- */
+
+/* Statevector.entangle statevec.py:302-315 -> _entangle_jit :915-937.
+ * With GXSV_OPT_FUSION >= 1 the CZ is queued and consecutive calls are fused
+ * into one diagonal phase pass at the next non-E call. */
+int gxsv_entangle(gxsv_t* h, int q1, int q2);
+/* force queued work onto the device */
+int gxsv_flush(gxsv_t* h);
+
+/* ---- X / Z / C: single-qubit 2x2 ------------------------------------ */
+
+/* Statevector.evolve_single statevec.py:317-332 -> _evolve_single_jit :943-986 */
+int gxsv_evolve_single(gxsv_t* h, int q, const double m[8]);
+/* Statevector.swap statevec.py:497-506 -> _swap_jit :890-912 (a relabel here) */
+int gxsv_swap(gxsv_t* h, int q1, int q2);
+/* Statevector.evolve statevec.py:361-395, k-qubit operator (2^k x 2^k row-major) */
+int gxsv_evolve(gxsv_t* h, int k, const int* qubits, const double* op);
+
+/* ---- M: probability and projection ---------------------------------- */
+
+/* Statevector.expectation_single statevec.py:334-359 -> _expectation_single_jit :992-1039
+ * out[0..1] = <psi| op_q |psi> (complex). Synchronous. */
+int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]);
+/* Statevector.project_qubit statevec.py:430-495 -> _project_qubit_jit :1160-1198:
+ * apply `m` on qubit q, keep the non-zero half, normalize, remove the qubit.
+ * GXSV_EZERONORM when both half-norms are <= atol.  norms (may be NULL)
+ * receives the two half-norms the reference computes (:1185). */
+int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double norms[2]);
+
+/* ---- finalize / read-out -------------------------------------------- */
+
+/* Statevector.permute statevec.py:544-550: new qubit i is old qubit perm[i] */
+int gxsv_permute(gxsv_t* h, const int* perm, int n);
+/* Statevector.flatten statevec.py:261-267: 2^nqubit complex128, qubit 0 = MSB, to HOST memory */
+int gxsv_flatten(gxsv_t* h, double* out_host);
+/* same, to DEVICE memory owned by the caller (2^nqubit complex128) */
+int gxsv_flatten_device(gxsv_t* h, void* out_device);
+/* |<a|b>|^2 on device — Statevector.fidelity statevec.py:552-568 */
+int gxsv_fidelity(gxsv_t* a, gxsv_t* b, double* out);
+/* <psi|psi> of the live state (1 for a normalized state) */
+int gxsv_norm2(gxsv_t* h, double* out);
+/* replace the state by 2^n host amplitudes in reference order (Statevector(data), statevec.py:93-216) */
+int gxsv_set_state(gxsv_t* h, int n, const double* vec_host);
+
+/* ---- plumbing -------------------------------------------------------- */
+
+int gxsv_sync(gxsv_t* h);
+int gxsv_stats(gxsv_t* h, gxsv_stats_t* out);
+int gxsv_reset_stats(gxsv_t* h);
+/* physical bit of each logical qubit (debug / tests), out has nqubit entries; -1 = not materialized */
+int gxsv_layout(gxsv_t* h, int* out);
+int gxsv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GXSV_H_ */

@@ -1,0 +1,69 @@
+"""Shared helpers for the parity tests."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+from graphix_b200 import mbqc
+from graphix_b200.pattern_io import load_pattern_dict, pattern_from_dict
+from graphix_b200.simulator import PatternSimulator
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+P_TOL = 1e-10          # north_star: per-measurement outcome probabilities within 1e-10
+F_TOL = 1e-10          # north_star: final-state fidelity >= 1 - 1e-10
+
+
+def golden_pattern_names(with_traces: bool = True) -> list[str]:
+    names = []
+    for p in sorted(glob.glob(os.path.join(GOLDEN, "patterns", "*.json.gz"))):
+        name = os.path.basename(p)[: -len(".json.gz")]
+        if with_traces and name.startswith(("config2", "config3", "config4", "rand20", "rand22")):
+            continue
+        names.append(name)
+    return names
+
+
+def load_golden(name: str) -> dict:
+    return load_pattern_dict(os.path.join(GOLDEN, "patterns", name + ".json.gz"))
+
+
+def decode_input(enc: dict):
+    if enc["kind"] == "plus":
+        return mbqc.BasicStates.PLUS
+    if enc["kind"] == "states":
+        return [mbqc.PlanarState(mbqc.Plane[p], a) for p, a in enc["states"]]
+    return np.asarray(enc["data"], dtype=np.float64).view(np.complex128)
+
+
+def make_selector(trace: dict) -> mbqc.BranchSelector:
+    """Replay the reference's recorded outcomes; p0 is recorded for every measurement."""
+    fixed = mbqc.FixedBranchSelector({int(k): v for k, v in trace["outcomes"].items()})
+    return mbqc.RecordingBranchSelector(fixed)
+
+
+def run_trace(d: dict, trace: dict, backend_factory):
+    """Run golden pattern ``d`` under ``trace``'s outcomes; returns (p0 dict, outcomes, final flat state)."""
+    pattern = pattern_from_dict(d)
+    sel = make_selector(trace)
+    backend = backend_factory(pattern.max_space(), sel)
+    sim = PatternSimulator(pattern, backend=backend)
+    sim.run(decode_input(trace["input"]))
+    return sel.p0, sim.measure_method.results, np.asarray(backend.state.flatten())
+
+
+def check_trace(d: dict, trace: dict, backend_factory) -> None:
+    p0, outcomes, flat = run_trace(d, trace, backend_factory)
+    for k, v in trace["p0"].items():
+        assert abs(p0[int(k)] - v) <= P_TOL, (k, p0[int(k)], v)
+    assert {str(k): int(v) for k, v in outcomes.items()} == trace["outcomes"]
+    ref = np.asarray(trace["final_state"], dtype=np.float64).view(np.complex128)
+    fid = abs(np.vdot(ref, flat)) ** 2
+    assert fid >= 1 - F_TOL, fid
+    assert abs(np.vdot(flat, flat).real - 1) <= 1e-10
+
+
+def rand_state(rng, n):
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    return v / np.linalg.norm(v)
