@@ -1,0 +1,83 @@
+"""Pattern-level parity: golden traces of the reference StatevectorBackend replayed on the B200 backend,
+in every fusion mode, plus direct comparison with the oracle under seeded random branch selection."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from helpers import F_TOL, P_TOL, check_trace, golden_pattern_names, load_golden
+
+from graphix_b200 import B200StatevectorBackend, PatternSimulator, mbqc
+from graphix_b200.pattern_io import pattern_from_dict
+from oracle.oracle import OracleBackend
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+@pytest.mark.parametrize("name", golden_pattern_names())
+def test_golden_traces(name, fusion):
+    d = load_golden(name)
+    for trace in d["traces"]:
+        check_trace(d, trace,
+                    lambda cap, sel: B200StatevectorBackend.with_capacity(cap, branch_selector=sel, fusion=fusion))
+
+
+@pytest.mark.parametrize("name", ["config1_rand8x5", "qaoa7", "rand11x6"])
+def test_random_branch_same_rng_as_oracle(name):
+    """RandomBranchSelector(pr_calc=True) with the same seed must take the same branch on both backends
+    (probabilities agree to 1e-10, so `rng.random() > p0` agrees) and end in the same state."""
+    d = load_golden(name)
+    pattern = pattern_from_dict(d)
+    out = []
+    for make in (lambda s: B200StatevectorBackend.with_capacity(pattern.max_space(), branch_selector=s),
+                 lambda s: OracleBackend.with_capacity(pattern.max_space(), branch_selector=s)):
+        rec = mbqc.RecordingBranchSelector(mbqc.RandomBranchSelector(pr_calc=True))
+        sim = PatternSimulator(pattern, backend=make(rec))
+        sim.run(rng=np.random.default_rng(123))
+        out.append((rec.p0, dict(sim.measure_method.results), np.asarray(sim.backend.state.flatten())))
+    (p_dev, r_dev, s_dev), (p_orc, r_orc, s_orc) = out
+    assert r_dev == r_orc
+    assert max(abs(p_dev[k] - p_orc[k]) for k in p_orc) <= P_TOL
+    assert abs(np.vdot(s_orc, s_dev)) ** 2 >= 1 - F_TOL
+
+
+def test_string_backend_and_simulator_contract():
+    """tests/test_simulator.py:16-75 of the reference: input-state rules, finalize leaves node_index == outputs."""
+    d = load_golden("config1_rand8x5")
+    pattern = pattern_from_dict(d)
+    sim = PatternSimulator(pattern, "b200", branch_selector=mbqc.ConstBranchSelector(0))
+    sim.run()
+    assert list(sim.backend.node_index) == pattern.output_nodes
+    with pytest.raises(ValueError):
+        sim.run()  # backend already holds qubits
+    with pytest.raises(ValueError):
+        PatternSimulator(pattern, B200StatevectorBackend(), branch_selector=mbqc.ConstBranchSelector(0))
+    b = B200StatevectorBackend(branch_selector=mbqc.ConstBranchSelector(0))
+    with pytest.raises(ValueError):
+        PatternSimulator(pattern, b).run(input_state=None)  # no pre-prepared inputs
+    with pytest.raises(ValueError):
+        B200StatevectorBackend(symbolic=True)
+    with pytest.raises(TypeError):
+        B200StatevectorBackend(None, mbqc.ConstBranchSelector(0))  # keyword-only (tests/test_statevec.py:525-537)
+
+
+def test_prepared_backend_input_state_none():
+    d = load_golden("handbuilt_allkinds")
+    pattern = pattern_from_dict(d)
+    trace = d["traces"][0]
+    from helpers import decode_input, make_selector
+
+    sel = make_selector(trace)
+    b = B200StatevectorBackend.with_capacity(pattern.max_space(), branch_selector=sel)
+    b.add_nodes(pattern.input_nodes, decode_input(trace["input"]))
+    PatternSimulator(pattern, b).run(input_state=None)
+    ref = np.asarray(trace["final_state"], dtype=np.float64).view(np.complex128)
+    assert abs(np.vdot(ref, b.state.flatten())) ** 2 >= 1 - F_TOL
+
+
+def test_noise_not_supported():
+    from graphix_b200.statevec import NoiseNotSupportedError
+
+    b = B200StatevectorBackend()
+    with pytest.raises(NoiseNotSupportedError):
+        b.apply_noise(None)

@@ -1,0 +1,272 @@
+"""Kernel-level parity of the CUDA path (through the C ABI) against golden vectors of the reference
+and against the oracle.  Mirrors the reference's tests/test_statevec.py:151-294, 449-480, 648-673."""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+import pytest
+from helpers import rand_state
+
+from graphix_b200 import B200Statevector, mbqc
+from oracle.oracle import OracleStatevector, outcome_to_operator_matrix
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-13
+
+
+def fid(a, b):
+    return abs(np.vdot(a, b)) ** 2
+
+
+def _sv(psi, cap=None, **kw):
+    return B200Statevector(psi, max_qubits=cap, **kw)
+
+
+@pytest.mark.parametrize("n", range(1, 7))
+def test_kernels_against_reference_golden(kernels_golden, n):
+    g = kernels_golden
+    psi, op = g[f"n{n}_psi"], g[f"n{n}_op"]
+    np.testing.assert_allclose(_sv(psi).flatten(), psi, atol=1e-15)
+    sv = _sv(psi, n + 2)
+    sv.add_nodes(1, mbqc.BasicStates.PLUS)
+    np.testing.assert_allclose(sv.flatten(), g[f"n{n}_addplus"], atol=TOL)
+    sv = _sv(psi)
+    sv.add_nodes(1, g[f"n{n}_s1"])
+    np.testing.assert_allclose(sv.flatten(), g[f"n{n}_add1"], atol=TOL)
+    sv = _sv(psi)
+    sv.add_nodes(2, g[f"n{n}_s2"])
+    np.testing.assert_allclose(sv.flatten(), g[f"n{n}_add2"], atol=TOL)
+    for q in range(n):
+        sv = _sv(psi)
+        sv.evolve_single(op, q)
+        np.testing.assert_allclose(sv.flatten(), g[f"n{n}_evolve_q{q}"], atol=TOL)
+        assert abs(_sv(psi).expectation_single(op, q) - complex(g[f"n{n}_expect_q{q}"])) < TOL
+        for r in (0, 1):
+            pm = g[f"n{n}_proj_q{q}_r{r}_op"]
+            sv = _sv(psi)
+            assert abs(sv.expectation_single(pm, q) - complex(g[f"n{n}_proj_q{q}_r{r}_p"])) < TOL
+            sv.project_qubit(pm, q)
+            assert sv.nqubit == n - 1
+            # same vector as the reference, phase included
+            np.testing.assert_allclose(sv.flatten(), g[f"n{n}_proj_q{q}_r{r}"], atol=1e-12)
+        if f"n{n}_projgen_q{q}" in g:
+            sv = _sv(psi)
+            sv.project_qubit(op, q)  # non-projector: literal two-pass reference algorithm
+            np.testing.assert_allclose(sv.flatten(), g[f"n{n}_projgen_q{q}"], atol=1e-12)
+        for q2 in range(n):
+            if q2 == q:
+                continue
+            sv = _sv(psi)
+            sv.entangle((q, q2))
+            np.testing.assert_array_equal(sv.flatten(), g[f"n{n}_cz_{q}_{q2}"])
+            sv = _sv(psi)
+            sv.swap((q, q2))
+            np.testing.assert_array_equal(sv.flatten(), g[f"n{n}_swap_{q}_{q2}"])
+    for t in range(3):
+        sv = _sv(psi)
+        sv.permute([int(x) for x in g[f"n{n}_perm{t}_p"]])
+        np.testing.assert_array_equal(sv.flatten(), g[f"n{n}_perm{t}"])
+
+
+def test_kernels_17_qubits_golden(kernels_golden):
+    g = kernels_golden
+    n = 17
+    psi = rand_state(np.random.default_rng(17), n)
+    w = rand_state(np.random.default_rng(1717), n + 1)
+    op = g["n17_op"]
+    for q in (0, 5, 16):
+        sv = _sv(psi)
+        sv.evolve_single(op, q)
+        assert abs(np.vdot(w[: 1 << n], sv.flatten()) - complex(g[f"n17_evolve_q{q}_dig"])) < 1e-12
+        assert abs(_sv(psi).expectation_single(op, q) - complex(g[f"n17_expect_q{q}"])) < 1e-11
+        sv = _sv(psi)
+        sv.project_qubit(g[f"n17_proj_q{q}_op"], q)
+        assert abs(np.vdot(w[: 1 << (n - 1)], sv.flatten()) - complex(g[f"n17_proj_q{q}_dig"])) < 1e-12
+    sv = _sv(psi)
+    sv.entangle((3, 11))
+    assert abs(np.vdot(w[: 1 << n], sv.flatten()) - complex(g["n17_cz_3_11_dig"])) < 1e-12
+    sv = _sv(psi, n + 1)
+    sv.add_nodes(1, mbqc.BasicStates.PLUS)
+    assert abs(np.vdot(w, sv.flatten()) - complex(g["n17_addplus_dig"])) < 1e-12
+
+
+@pytest.mark.parametrize("n", [9, 12, 14, 18])
+def test_every_axis_against_oracle(n):
+    """All kernels on every axis at sizes that cross the tile (11 bits) and hole (bit 8) boundaries."""
+    rng = np.random.default_rng(100 + n)
+    psi = rand_state(rng, n)
+    op = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    for q in range(n):
+        vec = rng.normal(size=3)
+        vec /= np.linalg.norm(vec)
+        pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
+        dev, orc = _sv(psi), OracleStatevector(psi)
+        assert abs(dev.expectation_single(pm, q) - orc.expectation_single(pm, q)) < 1e-12
+        dev.project_qubit(pm, q)
+        orc.project_qubit(pm, q)
+        np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-12)
+        # keep going on the shrunk state: layout now has a hole or a shifted tile
+        q2 = int(rng.integers(n - 1))
+        dev.evolve_single(op, q2)
+        orc.evolve_single(op, q2)
+        a, b = (int(x) for x in rng.choice(n - 1, size=2, replace=False))
+        dev.entangle((a, b))
+        orc.entangle((a, b))
+        dev.add_nodes(1, mbqc.BasicStates.PLUS)
+        orc.add_nodes(1, mbqc.BasicStates.PLUS)
+        dev.entangle((n - 1, a))
+        orc.entangle((n - 1, a))
+        np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-12)  # op is not unitary: both unnormalised alike
+
+
+def test_random_command_soup_against_oracle():
+    """Long random sequence of N / E-runs / M / 1q ops: exercises hole creation, hole filling,
+    tile shifts, extent trimming and the pending-scale bookkeeping together."""
+    rng = np.random.default_rng(2026)
+    n0 = 13
+    psi = rand_state(rng, n0)
+    dev, orc = _sv(psi, 16), OracleStatevector(psi, max_qubits=16)
+    for step in range(120):
+        n = orc.nqubit
+        kind = rng.choice(["N", "E", "M", "U", "Z"], p=[0.25, 0.3, 0.25, 0.1, 0.1])
+        if kind == "N" and n < 16:
+            st = [mbqc.BasicStates.PLUS, mbqc.BasicStates.ZERO, mbqc.BasicStates.ONE, mbqc.BasicStates.MINUS,
+                  mbqc.PlanarState(mbqc.Plane.YZ, 0.37)][int(rng.integers(5))]
+            dev.add_nodes(1, st)
+            orc.add_nodes(1, st)
+        elif kind == "E" and n >= 2:
+            for _ in range(int(rng.integers(1, 5))):
+                a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+                dev.entangle((a, b))
+                orc.entangle((a, b))
+        elif kind == "M" and n > 6:
+            q = int(rng.integers(n))
+            vec = rng.normal(size=3)
+            vec /= np.linalg.norm(vec)
+            pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
+            pd, po = dev.expectation_single(pm, q), orc.expectation_single(pm, q)
+            assert abs(pd - po) < 1e-10
+            dev.project_qubit(pm, q)
+            orc.project_qubit(pm, q)
+        elif kind == "U":
+            q = int(rng.integers(n))
+            m = mbqc.Clifford(int(rng.integers(24))).matrix
+            dev.evolve_single(m, q)
+            orc.evolve_single(m, q)
+        elif kind == "Z":
+            q = int(rng.integers(n))
+            m = [mbqc.Ops.Z, mbqc.Ops.X, mbqc.Ops.S][int(rng.integers(3))]
+            dev.evolve_single(m, q)
+            orc.evolve_single(m, q)
+        if step % 10 == 9:
+            assert dev.nqubit == orc.nqubit
+            np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
+    np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
+    assert abs(dev.norm2() - 1) < 1e-12
+
+
+def test_measure_all_then_regrow():
+    """Shrink to 0 qubits (scalar state) and grow again; capacity growth without with_capacity."""
+    sv = B200Statevector(nqubit=3, data=mbqc.BasicStates.PLUS)
+    proj0 = outcome_to_operator_matrix((0, 0, 1), 0)
+    for _ in range(3):
+        sv.project_qubit(proj0, 0)
+    assert sv.nqubit == 0
+    np.testing.assert_allclose(np.abs(sv.flatten()), [1.0], atol=1e-14)
+    for _ in range(5):
+        sv.add_nodes(1, mbqc.BasicStates.PLUS)
+    assert sv.max_qubits >= 5
+    np.testing.assert_allclose(np.abs(sv.flatten()), np.full(32, 1 / np.sqrt(32)), atol=1e-14)
+
+
+def test_zero_norm_projection_raises():
+    """tests/test_statevec.py:269-294 of the reference."""
+    sv = B200Statevector([mbqc.BasicStates.ZERO, mbqc.BasicStates.PLUS])
+    with pytest.raises(RuntimeError):
+        sv.project_qubit(outcome_to_operator_matrix((0, 0, 1), 1), 0)
+    sv = B200Statevector([mbqc.BasicStates.ONE, mbqc.BasicStates.PLUS])
+    sv.project_qubit(outcome_to_operator_matrix((0, 0, 1), 1), 0)
+    np.testing.assert_allclose(sv.flatten(), np.array([1, 1]) / np.sqrt(2), atol=1e-15)
+    # XY(1e-5) measured to outcome 1 has p ~ 2.5e-10, just above the cut-off (tests/test_branch_selector.py:152-168)
+    sv = B200Statevector([mbqc.BasicStates.PLUS, mbqc.BasicStates.PLUS])
+    v = mbqc.Plane.XY.polar(1e-5)
+    sv.project_qubit(outcome_to_operator_matrix(v, 1), 0)
+    assert abs(sv.norm2() - 1) < 1e-9
+
+
+def test_errors():
+    sv = B200Statevector(nqubit=2, data=mbqc.BasicStates.PLUS)
+    with pytest.raises(IndexError):
+        sv.evolve_single(np.eye(2), 2)
+    with pytest.raises(IndexError):
+        sv.entangle((0, 2))
+    with pytest.raises(IndexError):
+        sv.project_qubit(np.eye(2) / 2, -1)
+    with pytest.raises(ValueError):
+        sv.permute([0, 0])
+    with pytest.raises(ValueError):
+        sv.permute([0])
+    with pytest.raises(ValueError):
+        B200Statevector([1.0, 1.0])  # not normalised (statevec.py:196-197)
+    with pytest.raises(ValueError):
+        B200Statevector([1.0, 0.0, 0.0])  # not a power of two
+    with pytest.raises(NotImplementedError):
+        sv.remove_qubit(0)
+    with pytest.raises(TypeError):
+        sv.evolve_single(np.array([[1, 0], [0, object()]], dtype=object), 0)
+
+
+def test_permute_all_three_qubit_permutations():
+    """tests/test_statevec.py:648-673 of the reference: permute == transpose, bit exact."""
+    psi = rand_state(np.random.default_rng(9), 3)
+    for perm in itertools.permutations(range(3)):
+        sv = _sv(psi)
+        sv.permute(list(perm))
+        expect = np.transpose(psi.reshape(2, 2, 2), perm).reshape(8)
+        np.testing.assert_array_equal(sv.flatten(), expect)
+
+
+def test_all_cliffords_and_basic_states():
+    """tests/test_statevec.py:539-554 of the reference."""
+    for st in mbqc.BasicStates.VEC:
+        for k in range(24):
+            sv = B200Statevector(st)
+            sv.evolve_single(mbqc.Clifford(k).matrix, 0)
+            np.testing.assert_allclose(sv.flatten(), mbqc.Clifford(k).matrix @ st.to_statevector_numpy(), atol=1e-15)
+
+
+def test_to_dict_encoding():
+    """tests/test_statevec.py:423-447 of the reference."""
+    sv = B200Statevector([mbqc.BasicStates.ZERO, mbqc.BasicStates.ONE])
+    assert list(sv.to_dict()) == ["01"]
+    assert list(sv.to_dict(encoding="LSB")) == ["10"]
+    assert abs(sv.to_prob_dict()["01"] - 1) < 1e-15
+
+
+def test_fidelity_on_device():
+    psi = rand_state(np.random.default_rng(4), 10)
+    phi = rand_state(np.random.default_rng(5), 10)
+    a, b = _sv(psi), _sv(phi)
+    assert abs(a.fidelity(b) - fid(psi, phi)) < 1e-13
+    assert a.isclose(_sv(psi * np.exp(0.3j)))
+
+
+def test_large_state_roundtrip_properties():
+    """Size-independent properties at a size the oracle would take long for (24 -> 25 qubits):
+    N then M of the same qubit is the identity; CZ twice is the identity; norms stay 1."""
+    n = 24
+    sv = B200Statevector(nqubit=n, data=mbqc.BasicStates.PLUS, max_qubits=n + 1)
+    rng = np.random.default_rng(0)
+    for _ in range(6):
+        a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+        sv.entangle((a, b))
+        sv.evolve_single(mbqc.Clifford(int(rng.integers(24))).matrix, int(rng.integers(n)))
+    ref = B200Statevector(sv)  # device copy through flatten
+    sv.add_nodes(1, mbqc.BasicStates.PLUS)
+    sv.entangle((n, 3))
+    sv.entangle((3, n))
+    sv.project_qubit(outcome_to_operator_matrix((1, 0, 0), 0), n)
+    assert sv.nqubit == n
+    assert abs(sv.norm2() - 1) < 1e-12
+    assert abs(sv.fidelity(ref) - 1) < 1e-12
