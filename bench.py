@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 statevector pattern simulator (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--fusion F]
+
+A *step* is one complete pattern simulation (``PatternSimulator.run``: prepare inputs, every
+N/E/M/X/Z/C command, finalize) of the workload under ``ConstBranchSelector(0)``.
+
+* N = 1 : BASELINE config 2, ``rand_circuit(26, 20)`` space-minimised pattern, 3756 commands, 26<->27 live
+  qubits, complex128 (state 1-2 GiB, far larger than the 126 MB L2, so no flush is needed between steps).
+* N > 1 : (torchrun, one rank per GPU) the state is sharded by its top log2(N) qubits
+  (``graphix_b200.sharded``); weak scaling: the QFT pattern grows by one qubit per doubling of N.
+
+Prints ONE JSON line (rank 0).  ``value`` = commands/s with the inputs resident in HBM, timed with CUDA events
+on the launching stream (max over ranks); ``e2e`` = the same through the public call with HOST buffers (the
+input statevector is copied from pinned host memory and the final state is read back inside the timed region);
+``roofline`` = dominant kernel vs the measured HBM copy rate; ``cpu_baseline`` = the oracle port of the
+reference numba backend timed on this box's host cores over a bounded window of the same pattern.
+
+``--impl reference`` times that CPU port alone (all host threads, bounded window per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "pattern_sim_commands_per_s"
+UNIT = "commands/s"
+NOMINAL_HBM_GBS = 8000.0
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_for(n_gpus: int, name: str | None) -> str:
+    if name:
+        return name
+    if n_gpus == 1:
+        return "config2_rand26x20"
+    # weak scaling anchor: 29 + log2(N) circuit qubits (30.. live) so that every N fits any B200 pool quickly;
+    # the 33..36-live-qubit series of BASELINE config 4 is selected with --workload config4_qft32.. (128 GiB/GPU)
+    return {2: "config4_qft29", 4: "config4_qft29", 8: "config4_qft29"}.get(n_gpus, "config4_qft29")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+        self.thread = None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self) -> None:
+        assert self.proc is not None and self.proc.stdout is not None
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU reference arm (oracle port of the numba backend)
+# ---------------------------------------------------------------------------
+def cpu_window(pattern, n_cmds: int, steps: int, warmup: int):
+    """Time ``steps`` windows of ``n_cmds`` consecutive commands of ``pattern`` on the oracle backend.
+
+    Setup (untimed): the input qubits are prepared and the pattern is advanced until the live width first
+    reaches its maximum, so every timed command runs at the widths the GPU arm runs at."""
+    from graphix_b200 import mbqc
+    from graphix_b200.simulator import DefaultMeasureMethod
+    from oracle.oracle import OracleBackend
+
+    cmds = list(pattern)
+    backend = OracleBackend.with_capacity(pattern.max_space(), branch_selector=mbqc.ConstBranchSelector(0))
+    backend.add_nodes(pattern.input_nodes, mbqc.BasicStates.PLUS)
+    mm = DefaultMeasureMethod()
+
+    def run(cmd) -> None:
+        k = cmd.kind.name
+        if k == "N":
+            backend.add_nodes([cmd.node], cmd.state)
+        elif k == "E":
+            backend.entangle_nodes(cmd.nodes)
+        elif k == "M":
+            mm.measure(backend, cmd)
+        elif k in ("X", "Z"):
+            if mm.check_domain(cmd.domain):
+                backend.correct_byproduct(cmd)
+        elif k == "C":
+            backend.apply_clifford(cmd.node, cmd.clifford)
+
+    pos = 0
+    while backend.nqubit < pattern.max_space() and pos < len(cmds):
+        run(cmds[pos])
+        pos += 1
+    times = []
+    for s in range(warmup + steps):
+        if pos + n_cmds > len(cmds):
+            break
+        t0 = time.perf_counter()
+        for c in cmds[pos:pos + n_cmds]:
+            run(c)
+        dt = time.perf_counter() - t0
+        pos += n_cmds
+        if s >= warmup:
+            times.append(dt)
+    return times
+
+
+def reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern
+
+    name = workload_for(args.gpus, args.workload)
+    pattern = load_pattern(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
+    if pattern.max_space() > 31:
+        print(json.dumps({"impl": "reference", "metric": METRIC, "unit": UNIT, "value": None, "n_gpus": args.gpus,
+                          "unavailable": "reference is limited to 31 qubits (int32 kernel signatures, SURVEY.md §2.1)"}))
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    width = pattern.max_space()
+    n_cmds = args.cpu_window or max(3, min(30, int(round(12 * 2.0 ** (27 - width)))) if width >= 24 else 300)
+    times = cpu_window(pattern, n_cmds, args.steps, args.warmup)
+    if not times:
+        raise SystemExit("pattern too short for the requested window")
+    per_step = float(np.mean(times))
+    value = n_cmds / per_step
+    sample = f"{n_cmds} consecutive commands of {name} per step at {width - 1}<->{width} live qubits (bounded window)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": name, "selector": "ConstBranchSelector(0)", "commands_per_step": n_cmds},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def gpu_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 backend has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1 (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from graphix_b200 import B200StatevectorBackend, PatternSimulator, _lib, mbqc
+    from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern
+
+    name = workload_for(args.gpus, args.workload)
+    pattern = load_pattern(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
+    ncmd = len(pattern)
+    width = pattern.max_space()
+    selector = mbqc.ConstBranchSelector(0)
+
+    if world > 1:
+        from graphix_b200.sharded import ShardedStatevectorBackend
+
+        def make_backend():
+            return ShardedStatevectorBackend.with_capacity(width, branch_selector=selector, fusion=args.fusion)
+    else:
+        def make_backend():
+            return B200StatevectorBackend.with_capacity(width, branch_selector=selector, fusion=args.fusion,
+                                                        device=local_rank)
+
+    backend = make_backend()
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(profile: bool = False) -> None:
+        backend.state.reset()
+        backend.node_index.clear()
+        PatternSimulator(pattern, backend).run()
+
+    # ---- device-resident arm -------------------------------------------------
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    backend.state.reset_stats()
+    backend.state.set_option(_lib.OPT_PROFILE, 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    dev_ms = e0.elapsed_time(e1)
+    stats = backend.state.stats()
+    backend.state.set_option(_lib.OPT_PROFILE, 0)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = ncmd * args.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end arm: host input vector in, host final state out ------------
+    e2e = None
+    if world == 1:
+        n_in = len(pattern.input_nodes)
+        n_out = len(pattern.output_nodes)
+        host_in = torch.full((1 << n_in,), 2.0 ** (-n_in / 2), dtype=torch.complex128).pin_memory()
+        host_out = torch.empty(1 << n_out, dtype=torch.complex128).pin_memory()
+        np_in, np_out = host_in.numpy(), host_out.numpy()
+
+        def e2e_step() -> None:
+            backend.state.reset()
+            backend.node_index.clear()
+            PatternSimulator(pattern, backend).run(input_state=np_in)   # H2D of the input state inside
+            backend.state.flatten(out=np_out)                             # D2H of the result inside
+
+        e2e_step()
+        barrier()
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+        e2e = {"value": ncmd * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": 16 << n_in, "d2h_bytes_per_step": 16 << n_out,
+               "ms_per_step": e2e_ms / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------
+    peak, peak_src = measured_peak()
+    kinds = {k: v for k, v in stats.items() if v["launches"]}
+    dom = max(kinds, key=lambda k: kinds[k]["device_ms"])
+    d = kinds[dom]
+    achieved = d["algo_bytes"] / (d["device_ms"] * 1e-3) / 1e9
+    total_kernel_ms = sum(v["device_ms"] for v in kinds.values())
+    total_bytes = sum(v["algo_bytes"] for v in kinds.values())
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / NOMINAL_HBM_GBS,
+        "traffic": None,
+        "algo_bytes_per_launch": d["algo_bytes"] / d["launches"], "avg_launch_ms": d["device_ms"] / d["launches"],
+        "share_of_kernel_time": d["device_ms"] / total_kernel_ms,
+        "all_kernels_achieved": total_bytes / (total_kernel_ms * 1e-3) / 1e9,
+        "all_kernels_frac": total_bytes / (total_kernel_ms * 1e-3) / 1e9 / peak,
+        "kernel_time_share_of_step": total_kernel_ms / dev_ms,
+    }
+    per_kind = {k: {"launches_per_step": v["launches"] / args.steps, "ms_per_launch": v["device_ms"] / v["launches"],
+                    "GBps": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9 if v["device_ms"] else None}
+                for k, v in kinds.items()}
+
+    # ---- CPU baseline: the oracle port on this box's cores, bounded window --------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu and width <= 31:
+        cores = os.cpu_count() or 1
+        n_cmds = args.cpu_window or max(3, min(30, int(round(12 * 2.0 ** (27 - width)))) if width >= 24 else 300)
+        times = cpu_window(pattern, n_cmds, 1, 0)
+        if times:
+            cpu_baseline = {"value": n_cmds / times[0], "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{n_cmds} consecutive commands of {name} at {width - 1}<->{width} live qubits, "
+                                      f"{times[0]:.1f} s of CPU work"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "c128", "data": "synthetic",
+        "config": {"workload": name, "commands_per_step": ncmd, "live_qubits": f"{width - 1}<->{width}",
+                   "state_bytes_max": 16 << (width if world == 1 else width), "selector": "ConstBranchSelector(0)",
+                   "fusion": args.fusion, "parallelism": f"shard{world}" if world > 1 else "single",
+                   "l2": "state >> 126 MB L2: inputs larger than L2, no flush needed"},
+        "e2e": e2e, "gpu_launches": int(sum(v["launches"] for v in kinds.values())),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": per_kind,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, help="pattern fixture name under tests/golden/patterns")
+    ap.add_argument("--fusion", type=int, default=1)
+    ap.add_argument("--cpu-window", type=int, default=0, help="commands per CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

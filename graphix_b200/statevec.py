@@ -106,6 +106,19 @@ class B200Statevector:
         if _is_state(data):
             n = 1 if nqubit is None else nqubit
             return [data] * n, n
+        if isinstance(data, np.ndarray) and data.ndim == 1 and data.dtype.kind in "fc" and data.size > 0:
+            # numeric vector fast path (no Python list of 2^n scalars); same checks as statevec.py:188-197
+            length = int(data.size)
+            inferred = length.bit_length() - 1
+            if nqubit is None:
+                if length & (length - 1):
+                    raise ValueError(f"Length of input data is not a power of two: {length}.")
+            elif nqubit != inferred:
+                raise ValueError(f"Mismatch between nqubit and inferred nqubit: {nqubit} != {inferred}.")
+            psi = np.ascontiguousarray(data, dtype=np.complex128)
+            if not np.isclose(math.sqrt(np.vdot(psi, psi).real), 1.0):
+                raise ValueError("Input state is not normalized.")
+            return psi, inferred
         if not isinstance(data, Iterable):
             raise TypeError(f"Incorrect type for data: {type(data)}.")
         items = list(data)
@@ -177,9 +190,15 @@ class B200Statevector:
         """statevec.py:243-259."""
         self._check(self._lib.gxsv_ensure_capacity(self._h, int(required_qubits)))
 
-    def flatten(self) -> np.ndarray:
-        """2**nqubit complex128 on the host, qubit 0 = MSB — statevec.py:261-267."""
-        out = np.empty(1 << self.nqubit, dtype=np.complex128)
+    def flatten(self, out: np.ndarray | None = None) -> np.ndarray:
+        """2**nqubit complex128 on the host, qubit 0 = MSB — statevec.py:261-267.
+
+        ``out`` (optional) is a preallocated C-contiguous complex128 array, e.g. pinned memory."""
+        size = 1 << self.nqubit
+        if out is None:
+            out = np.empty(size, dtype=np.complex128)
+        elif out.dtype != np.complex128 or out.size != size or not out.flags.c_contiguous:
+            raise ValueError(f"`out` must be a C-contiguous complex128 array of {size} elements")
         self._check(self._lib.gxsv_flatten(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 
