@@ -29,11 +29,11 @@ constexpr int HOLE_MIN = 8;     // dead bits are only ever created at physical b
 constexpr int TILE_BITS = 11;   // k_contract<4,true>: a CTA tile spans the lowest 11 live bits
 constexpr int U_DEF = 4;
 constexpr int RING = 256;
-constexpr int MAX_GRID = 148 * 8;
 constexpr int GXSV_VERSION = 100;
 
 struct Qubit {
-  int phys;     // physical bit, -1 while virtual (lazy mode)
+  int id;       // stable identity (queued CZs refer to ids: logical indices shift, tiles relocate bits)
+  int phys;     // physical bit, -1 while virtual (lazy mode: prepared but not yet materialised)
   cplx s0, s1;  // single-qubit state while virtual
 };
 
@@ -53,7 +53,8 @@ struct gxsv {
   int phys_bits = 0;       // all live physical bits are < phys_bits
   uint64_t live_mask = 0;  // set bits = physical bits carrying a materialised qubit
   std::vector<Qubit> q;    // logical order (reference order: index 0 = MSB)
-  std::vector<std::pair<int, int>> pend;  // queued CZs as (physical bit, physical bit)
+  std::vector<std::pair<int, int>> pend;  // queued CZs as (qubit id, qubit id)
+  int next_id = 0;
   cplx hscale = 1.0;       // host part of the pending scalar: true psi = g(device) * hscale * stored
   // device control + result ring
   Ctrl* ctrl = nullptr;
@@ -223,17 +224,43 @@ int check_q(gxsv_t* h, int q) {
 
 double state_bytes(const gxsv_t* h) { return 16.0 * std::ldexp(1.0, nlive_bits(h)); }
 
-// --- E-run flush ------------------------------------------------------------
-int flush_pending(gxsv_t* h) {
-  if (h->pend.empty()) return GXSV_OK;
-  // CZ^2 = 1: cancel duplicates
+// --- queued CZs --------------------------------------------------------------
+Qubit* by_id(gxsv_t* h, int id) {
+  for (auto& qb : h->q) if (qb.id == id) return &qb;
+  return nullptr;
+}
+
+// CZ^2 = 1: canonical order, cancel duplicates
+void dedupe_pending(gxsv_t* h) {
   std::vector<std::pair<int, int>> edges;
   for (auto e : h->pend) {
     if (e.first > e.second) std::swap(e.first, e.second);
     auto it = std::find(edges.begin(), edges.end(), e);
     if (it != edges.end()) edges.erase(it); else edges.push_back(e);
   }
-  h->pend.clear();
+  h->pend.swap(edges);
+}
+
+// Issue the queued CZs whose two qubits are materialised (all of them, or only those touching
+// qubit `touching` when >= 0) as diagonal phase passes: stars sharing a pivot go through
+// k_cz_star (touches a quarter of the amplitudes), anything else through one general pass.
+int flush_real_edges(gxsv_t* h, int touching = -1) {
+  if (h->pend.empty()) return GXSV_OK;
+  dedupe_pending(h);
+  std::vector<std::pair<int, int>> edges, keep;
+  for (auto& e : h->pend) {
+    Qubit* a = by_id(h, e.first);
+    Qubit* b = by_id(h, e.second);
+    const bool real = a && b && a->phys >= 0 && b->phys >= 0;
+    if (real && (touching < 0 || e.first == touching || e.second == touching)) {
+      int pa = a->phys, pb = b->phys;
+      if (pa > pb) std::swap(pa, pb);
+      edges.push_back({pa, pb});
+    } else {
+      keep.push_back(e);
+    }
+  }
+  h->pend.swap(keep);
   const int n = nlive_bits(h);
   const double S = state_bytes(h);
   while (!edges.empty()) {
@@ -296,11 +323,13 @@ int alloc_bit(gxsv_t* h, int* bit) {
   return GXSV_OK;
 }
 
-int add_one(gxsv_t* h, cplx s0, cplx s1) {
-  int rc = flush_pending(h);
-  if (rc) return rc;
+// Give the virtual qubit at logical index qi a physical bit (k_fill): psi <- psi (x) (s0, s1).
+int materialize(gxsv_t* h, int qi) {
+  Qubit& qb = h->q[qi];
+  if (qb.phys >= 0) return GXSV_OK;
+  const cplx s0 = qb.s0, s1 = qb.s1;
   int hb;
-  rc = alloc_bit(h, &hb);
+  int rc = alloc_bit(h, &hb);
   if (rc) return rc;
   const int n = nlive_bits(h);
   const uint64_t nlive = 1ull << n;
@@ -328,13 +357,52 @@ int add_one(gxsv_t* h, cplx s0, cplx s1) {
   if (rc) return rc;
   h->live_mask |= 1ull << hb;
   if (hb >= h->phys_bits) h->phys_bits = hb + 1;
-  h->q.push_back({hb, 0.0, 0.0});
+  h->q[qi].phys = hb;
   return GXSV_OK;
+}
+
+// everything queued goes to the device: all virtual qubits, then all CZs
+int flush_pending(gxsv_t* h) {
+  for (size_t i = 0; i < h->q.size(); ++i) {
+    int rc = materialize(h, (int)i);
+    if (rc) return rc;
+  }
+  return flush_real_edges(h, -1);
+}
+
+bool has_edge(const gxsv_t* h, int id) {
+  for (auto& e : h->pend) if (e.first == id || e.second == id) return true;
+  return false;
+}
+
+// Make qubit qi ready for an arbitrary (non-diagonal) operation: materialise it and its virtual
+// CZ partners, then issue the CZs that touch it.  Queued work elsewhere stays queued.
+int settle(gxsv_t* h, int qi) {
+  if (h->fusion < 2) return flush_pending(h);
+  dedupe_pending(h);
+  const int id = h->q[qi].id;
+  int rc = materialize(h, qi);
+  if (rc) return rc;
+  for (auto& e : h->pend) {
+    if (e.first != id && e.second != id) continue;
+    const int other = (e.first == id) ? e.second : e.first;
+    for (size_t i = 0; i < h->q.size(); ++i)
+      if (h->q[i].id == other) { rc = materialize(h, (int)i); if (rc) return rc; }
+  }
+  return flush_real_edges(h, id);
+}
+
+int add_one(gxsv_t* h, cplx s0, cplx s1) {
+  h->q.push_back({h->next_id++, -1, s0, s1});
+  if (h->fusion >= 2) return GXSV_OK;  // lazy: stays virtual until something needs it
+  int rc = flush_real_edges(h, -1);
+  if (rc) return rc;
+  return materialize(h, (int)h->q.size() - 1);
 }
 
 // Launch the contraction of physical bit p with bra (c0, c1) (host scalar already folded in by
 // the caller) and update the layout.  `qidx` = logical index of the measured qubit.
-int launch_contract(gxsv_t* h, int qidx, cplx c0, cplx c1, unsigned long long* seq_out) {
+int launch_contract(gxsv_t* h, int qidx, cplx c0, cplx c1, uint64_t mq, unsigned long long* seq_out) {
   const int p = h->q[qidx].phys;
   const int n = nlive_bits(h);
   const uint64_t nout = 1ull << (n - 1);
@@ -350,8 +418,8 @@ int launch_contract(gxsv_t* h, int qidx, cplx c0, cplx c1, unsigned long long* s
     const int grid = grid_for(h, nout, U_DEF);
     {
       Launch Lc(h, GXSV_K_CONTRACT, 1.5 * S);
-      k_contract<U_DEF, false><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hs, p, d2(c0), d2(c1), nout, h->partials,
-                                                           h->ctrl, slot, seq);
+      k_contract<U_DEF, false><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hs, p, d2(c0), d2(c1), mq, nout,
+                                                           h->partials, h->ctrl, slot, seq);
     }
     h->live_mask &= ~(1ull << p);
   } else {
@@ -365,8 +433,8 @@ int launch_contract(gxsv_t* h, int qidx, cplx c0, cplx c1, unsigned long long* s
     const int grid = grid_for(h, nout, U_DEF);
     {
       Launch Lc(h, GXSV_K_CONTRACT, 1.5 * S);
-      k_contract<U_DEF, true><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hd, p, d2(c0), d2(c1), nout, h->partials,
-                                                          h->ctrl, slot, seq);
+      k_contract<U_DEF, true><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hd, p, d2(c0), d2(c1), mq, nout,
+                                                          h->partials, h->ctrl, slot, seq);
     }
     // qubits on L[t+1 .. K-1] slide down one live slot
     for (auto& qb : h->q) {
@@ -504,6 +572,7 @@ int gxsv_reset(gxsv_t* h) {
   CU(cudaSetDevice(h->device));
   h->q.clear();
   h->pend.clear();
+  h->next_id = 0;
   h->phys_bits = 0;
   h->live_mask = 0;
   h->hscale = 1.0;
@@ -599,7 +668,7 @@ int gxsv_tensor(gxsv_t* h, int k, const double* vec) {
     h->stats.algo_bytes[GXSV_K_TENSOR] += 16.0 * (double)nnew;
     h->phys_bits = k;
     h->live_mask = nnew - 1ull;
-    for (int j = 0; j < k; ++j) h->q.push_back({k - 1 - j, 0.0, 0.0});
+    for (int j = 0; j < k; ++j) h->q.push_back({h->next_id++, k - 1 - j, 0.0, 0.0});
     // the previous scalar psi[0]*g*hscale keeps living in hscale/g (psi[0] was 1 by construction after reset/M)
     return GXSV_OK;
   }
@@ -632,7 +701,7 @@ int gxsv_tensor(gxsv_t* h, int k, const double* vec) {
   if (rc) return rc;
   h->live_mask = mask;
   h->phys_bits = extent;
-  for (int j = 0; j < k; ++j) h->q.push_back({(int)nb.pos[j], 0.0, 0.0});
+  for (int j = 0; j < k; ++j) h->q.push_back({h->next_id++, (int)nb.pos[j], 0.0, 0.0});
   return GXSV_OK;
 }
 
@@ -648,7 +717,7 @@ int gxsv_entangle(gxsv_t* h, int q1, int q2) {
   rc = check_q(h, q2);
   if (rc) return rc;
   if (q1 == q2) return fail(h, GXSV_EVALUE, "entangle: control and target must differ");
-  h->pend.push_back({h->q[q1].phys, h->q[q2].phys});
+  h->pend.push_back({h->q[q1].id, h->q[q2].id});
   if (h->fusion == 0) { CU(cudaSetDevice(h->device)); return flush_pending(h); }
   return GXSV_OK;
 }
@@ -662,16 +731,29 @@ int gxsv_evolve_single(gxsv_t* h, int q, const double m[8]) {
   CU(cudaSetDevice(h->device));
   int rc = check_q(h, q);
   if (rc) return rc;
-  rc = flush_pending(h);
-  if (rc) return rc;
   const cplx m00(m[0], m[1]), m01(m[2], m[3]), m10(m[4], m[5]), m11(m[6], m[7]);
+  const bool diagonal = (m01 == cplx(0.0) && m10 == cplx(0.0));
+  if (h->fusion >= 2) {
+    Qubit& qb = h->q[q];
+    if (qb.phys < 0 && (diagonal || !has_edge(h, qb.id))) {
+      // still virtual: a diagonal op commutes with its queued CZs, any op does if it has none
+      const cplx a = qb.s0, b = qb.s1;
+      qb.s0 = m00 * a + m01 * b;
+      qb.s1 = m10 * a + m11 * b;
+      return GXSV_OK;
+    }
+    if (qb.phys < 0 || !diagonal) rc = settle(h, q);
+  } else {
+    rc = flush_pending(h);
+  }
+  if (rc) return rc;
   const int p = h->q[q].phys;
   const int n = nlive_bits(h);
   const uint64_t npair = 1ull << (n - 1);
   const double S = state_bytes(h);
   Holes hs = make_holes(h, p);
   const int grid = grid_for(h, npair, U_DEF);
-  if (m01 == cplx(0.0) && m10 == cplx(0.0) && std::abs(m00) > 0.0) {
+  if (diagonal && std::abs(m00) > 0.0) {
     // diagonal: fold m00 into the host scalar, scale only the bit = 1 half
     const cplx f = m11 / m00;
     h->hscale *= m00;
@@ -705,7 +787,7 @@ int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) 
   CU(cudaSetDevice(h->device));
   int rc = check_q(h, q);
   if (rc) return rc;
-  rc = flush_pending(h);
+  rc = settle(h, q);  // CZs not touching q and virtual qubits not entangled with q do not change <op_q>
   if (rc) return rc;
   const int p = h->q[q].phys;
   const int n = nlive_bits(h);
@@ -733,25 +815,82 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
   CU(cudaSetDevice(h->device));
   int rc = check_q(h, q);
   if (rc) return rc;
-  rc = flush_pending(h);
-  if (rc) return rc;
   const cplx m00(m[0], m[1]), m01(m[2], m[3]), m10(m[4], m[5]), m11(m[6], m[7]);
   const double r0 = std::norm(m00) + std::norm(m01), r1 = std::norm(m10) + std::norm(m11);
   if (r0 + r1 == 0.0) return fail(h, GXSV_EZERONORM, "Attempted to remove qubit %d from 0-norm statevector.", q);
   const double det = std::abs(m00 * m11 - m01 * m10);
   const bool rank1 = det <= 1e-13 * (r0 + r1);
-  const int p = h->q[q].phys;
-  const int n = nlive_bits(h);
   double v[4];
   unsigned long long seq;
   if (rank1) {
     // op = u w^T: row r = u_r * w.  Contract with the larger row (best conditioned); the two half-norms the
     // reference computes (statevec.py:1185) differ from it only by the known factor |u_r|^2/|u_big|^2.
     const int big = (r0 >= r1) ? 0 : 1;
-    const cplx c0 = big ? m10 : m00, c1 = big ? m11 : m01;
+    const cplx c0 = (big ? m10 : m00) * h->hscale, c1 = (big ? m11 : m01) * h->hscale;
     const double rbig = big ? r1 : r0;
-    rc = launch_contract(h, q, c0 * h->hscale, c1 * h->hscale, &seq);
-    if (rc) return rc;
+    if (h->fusion < 2) {
+      rc = flush_pending(h);
+      if (rc) return rc;
+      rc = launch_contract(h, q, c0, c1, 0ull, &seq);
+      if (rc) return rc;
+    } else {
+      // lazy mode: the CZs queued on q are applied inside the projection pass, and one virtual
+      // partner of q is materialised by the same pass (k_fused)
+      if (h->q[q].phys < 0) { rc = settle(h, q); if (rc) return rc; }
+      dedupe_pending(h);
+      const int qid = h->q[q].id;
+      std::vector<int> virt;  // logical indices of virtual partners
+      for (auto& e : h->pend) {
+        if (e.first != qid && e.second != qid) continue;
+        const int other = (e.first == qid) ? e.second : e.first;
+        for (size_t i = 0; i < h->q.size(); ++i)
+          if (h->q[i].id == other && h->q[i].phys < 0) virt.push_back((int)i);
+      }
+      int vi = -1;
+      if (!virt.empty()) {
+        vi = virt.back();
+        virt.pop_back();
+        for (int i : virt) { rc = materialize(h, i); if (rc) return rc; }
+      }
+      const int vid = (vi >= 0) ? h->q[vi].id : -1;
+      uint64_t mq = 0, mv = 0;
+      std::vector<std::pair<int, int>> keep;
+      for (auto& e : h->pend) {
+        const bool tq = (e.first == qid || e.second == qid);
+        const bool tv = (vid >= 0) && (e.first == vid || e.second == vid);
+        if (tq && tv) continue;  // the (q, v) edge itself: consumed by the butterfly
+        if (tq) {
+          mq |= 1ull << by_id(h, e.first == qid ? e.second : e.first)->phys;
+        } else if (tv) {
+          Qubit* o = by_id(h, e.first == vid ? e.second : e.first);
+          if (o->phys >= 0) mv |= 1ull << o->phys; else keep.push_back(e);  // virtual-virtual edges stay queued
+        } else {
+          keep.push_back(e);
+        }
+      }
+      h->pend.swap(keep);
+      if (vi < 0) {
+        rc = launch_contract(h, q, c0, c1, mq, &seq);
+        if (rc) return rc;
+      } else {
+        const int p = h->q[q].phys;
+        const cplx s0 = h->q[vi].s0, s1 = h->q[vi].s1;
+        const int n = nlive_bits(h);
+        const uint64_t npair = 1ull << (n - 1);
+        Holes hs = make_holes(h, p);
+        Res* slot = next_slot(h, &seq);
+        {
+          Launch L(h, GXSV_K_FUSED, 2.0 * state_bytes(h));
+          k_fused<U_DEF><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(
+              h->psi, hs, p, d2(s0 * c0), d2(s0 * c1), d2(s1 * c0), d2(-s1 * c1), mq, mv, npair, h->partials, h->ctrl,
+              slot, seq);
+        }
+        rc = check_launch(h, "k_fused");
+        if (rc) return rc;
+        h->q[vi].phys = p;  // the new qubit takes over the measured qubit's physical bit
+        h->q.erase(h->q.begin() + q);
+      }
+    }
     h->hscale = 1.0;
     if (!h->strict) {
       if (norms) { norms[0] = norms[1] = NAN; }
@@ -777,6 +916,10 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     return GXSV_OK;
   }
   // general 2x2 (not a projector): literal two-pass reference algorithm
+  rc = settle(h, q);
+  if (rc) return rc;
+  const int p = h->q[q].phys;
+  const int n = nlive_bits(h);
   const uint64_t npair = 1ull << (n - 1);
   Holes hs = make_holes(h, p);
   Res* slot = next_slot(h, &seq);
@@ -796,7 +939,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     pick = 1;
     if (v[1] <= atol) return fail(h, GXSV_EZERONORM, "Attempted to remove qubit %d from 0-norm statevector.", q);
   }
-  rc = launch_contract(h, q, (pick ? m10 : m00) * h->hscale, (pick ? m11 : m01) * h->hscale, &seq);
+  rc = launch_contract(h, q, (pick ? m10 : m00) * h->hscale, (pick ? m11 : m01) * h->hscale, 0ull, &seq);
   if (rc) return rc;
   h->hscale = 1.0;
   if (h->strict) rc = wait_slot(h, seq, v);

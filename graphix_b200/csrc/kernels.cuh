@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(TPB) k_diag_edges(double2* __restrict__ psi, c
 // M — project + compact + reduce in one pass:
 //   out[j] = g*(c0*psi[s0(j)] + c1*psi[s0(j)|p]),  norm2 = sum |out|^2
 // s0 inserts the layout holes and the measured bit p (hs); the result is
-// written at d(j) (hd).  TILE = false: d == s0, the measured bit becomes a
+// written at d(j) (hd).  `mq` (physical-bit mask) carries CZs still queued
+// between the measured qubit and other qubits: they are applied on the fly.  TILE = false: d == s0, the measured bit becomes a
 // hole (p >= 8).  TILE = true: p is a low bit; each CTA owns one aligned tile
 // of the lowest K live bits, reads all 2^K inputs into registers, barriers,
 // and writes the 2^(K-1) outputs into the lower half of its own tile, so the
@@ -255,8 +256,9 @@ __global__ void __launch_bounds__(TPB) k_diag_edges(double2* __restrict__ psi, c
 template <int U, bool TILE>
 __global__ void __launch_bounds__(TPB) k_contract(double2* __restrict__ psi, const __grid_constant__ Holes hs,
                                                   const __grid_constant__ Holes hd, const int pbit, double2 c0,
-                                                  double2 c1, const uint64_t nout, double* __restrict__ partials,
-                                                  Ctrl* ctrl, Res* res, const unsigned long long seq) {
+                                                  double2 c1, const uint64_t mq, const uint64_t nout,
+                                                  double* __restrict__ partials, Ctrl* ctrl, Res* res,
+                                                  const unsigned long long seq) {
   const double g = ctrl->g;
   c0.x *= g; c0.y *= g; c1.x *= g; c1.y *= g;
   const uint64_t chunk = (uint64_t)TPB * U;
@@ -279,10 +281,64 @@ __global__ void __launch_bounds__(TPB) k_contract(double2* __restrict__ psi, con
     for (int u = 0; u < U; ++u) {
       const uint64_t j = base + (uint64_t)u * TPB + threadIdx.x;
       if (j < nout) {
-        const double2 r = cmad2(c0, a[u], c1, b[u]);
+        // queued CZs between the measured qubit and the qubits in mq: sign on the x_p = 1 amplitude
+        const double sg = (__popcll(s[u] & mq) & 1) ? -1.0 : 1.0;
+        const double2 r = cmad2(c0, a[u], c1, make_double2(sg * b[u].x, sg * b[u].y));
         acc[0] += cnorm2(r);
         const uint64_t d = TILE ? expand(j, hd) : s[u];
         st_amp(psi + d, r);
+      }
+    }
+  }
+  grid_finish<1>(acc, partials, ctrl, res, seq, FIN_CONTRACT, 1.0, g);
+}
+
+// ---------------------------------------------------------------------------
+// Lazy N,E..,M fusion.  A qubit v that was prepared (state (s0,s1)) and entangled
+// with the measured qubit q but never materialised takes q's physical bit:
+//   t0 = psi[x, q=0],  t1 = sq(x) * psi[x, q=1]            sq = (-1)^{parity(x & mq)}
+//   psi'[x, v=0] =          m00*t0 + m01*t1                m = [[s0 c0, s0 c1], [s1 c0, -s1 c1]]
+//   psi'[x, v=1] = sv(x) * (m10*t0 + m11*t1)               sv = (-1)^{parity(x & mv)}
+// with <c| the measurement bra, mq / mv the queued CZ partners of q / v.
+// One in-place butterfly: reads S, writes S (instead of N 2S + E S/2 + M 3S at the
+// wider width), no hole is created and the norm is reduced in the same pass.
+// ---------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+                                               const int pbit, double2 m00, double2 m01, double2 m10, double2 m11,
+                                               const uint64_t mq, const uint64_t mv, const uint64_t npair,
+                                               double* __restrict__ partials, Ctrl* ctrl, Res* res,
+                                               const unsigned long long seq) {
+  const double g = ctrl->g;
+  m00.x *= g; m00.y *= g; m01.x *= g; m01.y *= g; m10.x *= g; m10.y *= g; m11.x *= g; m11.y *= g;
+  const uint64_t chunk = (uint64_t)TPB * U;
+  const uint64_t poff = 1ull << pbit;
+  double acc[1] = {0.0};
+  for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < npair; base += (uint64_t)gridDim.x * chunk) {
+    double2 a[U], b[U];
+    uint64_t s[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t j = base + (uint64_t)u * TPB + threadIdx.x;
+      s[u] = expand(j, hs);
+      if (j < npair) {
+        a[u] = ld_amp(psi + s[u]);
+        b[u] = ld_amp(psi + s[u] + poff);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t j = base + (uint64_t)u * TPB + threadIdx.x;
+      if (j < npair) {
+        const double sq = (__popcll(s[u] & mq) & 1) ? -1.0 : 1.0;
+        const double sv = (__popcll(s[u] & mv) & 1) ? -1.0 : 1.0;
+        const double2 t1 = make_double2(sq * b[u].x, sq * b[u].y);
+        const double2 r0 = cmad2(m00, a[u], m01, t1);
+        double2 r1 = cmad2(m10, a[u], m11, t1);
+        r1.x *= sv; r1.y *= sv;
+        acc[0] += cnorm2(r0) + cnorm2(r1);
+        st_amp(psi + s[u], r0);
+        st_amp(psi + s[u] + poff, r1);
       }
     }
   }

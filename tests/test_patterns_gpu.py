@@ -13,7 +13,7 @@ from oracle.oracle import OracleBackend
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("fusion", [0, 1])
+@pytest.mark.parametrize("fusion", [0, 1, 2])
 @pytest.mark.parametrize("name", golden_pattern_names())
 def test_golden_traces(name, fusion):
     d = load_golden(name)
@@ -22,14 +22,15 @@ def test_golden_traces(name, fusion):
                     lambda cap, sel: B200StatevectorBackend.with_capacity(cap, branch_selector=sel, fusion=fusion))
 
 
+@pytest.mark.parametrize("fusion", [1, 2])
 @pytest.mark.parametrize("name", ["config1_rand8x5", "qaoa7", "rand11x6"])
-def test_random_branch_same_rng_as_oracle(name):
+def test_random_branch_same_rng_as_oracle(name, fusion):
     """RandomBranchSelector(pr_calc=True) with the same seed must take the same branch on both backends
     (probabilities agree to 1e-10, so `rng.random() > p0` agrees) and end in the same state."""
     d = load_golden(name)
     pattern = pattern_from_dict(d)
     out = []
-    for make in (lambda s: B200StatevectorBackend.with_capacity(pattern.max_space(), branch_selector=s),
+    for make in (lambda s: B200StatevectorBackend.with_capacity(pattern.max_space(), branch_selector=s, fusion=fusion),
                  lambda s: OracleBackend.with_capacity(pattern.max_space(), branch_selector=s)):
         rec = mbqc.RecordingBranchSelector(mbqc.RandomBranchSelector(pr_calc=True))
         sim = PatternSimulator(pattern, backend=make(rec))

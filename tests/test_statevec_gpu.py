@@ -91,8 +91,9 @@ def test_kernels_17_qubits_golden(kernels_golden):
     assert abs(np.vdot(w, sv.flatten()) - complex(g["n17_addplus_dig"])) < 1e-12
 
 
+@pytest.mark.parametrize("fusion", [1, 2])
 @pytest.mark.parametrize("n", [9, 12, 14, 18])
-def test_every_axis_against_oracle(n):
+def test_every_axis_against_oracle(n, fusion):
     """All kernels on every axis at sizes that cross the tile (11 bits) and hole (bit 8) boundaries."""
     rng = np.random.default_rng(100 + n)
     psi = rand_state(rng, n)
@@ -101,7 +102,7 @@ def test_every_axis_against_oracle(n):
         vec = rng.normal(size=3)
         vec /= np.linalg.norm(vec)
         pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
-        dev, orc = _sv(psi), OracleStatevector(psi)
+        dev, orc = _sv(psi, fusion=fusion), OracleStatevector(psi)
         assert abs(dev.expectation_single(pm, q) - orc.expectation_single(pm, q)) < 1e-12
         dev.project_qubit(pm, q)
         orc.project_qubit(pm, q)
@@ -120,14 +121,16 @@ def test_every_axis_against_oracle(n):
         np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-12)  # op is not unitary: both unnormalised alike
 
 
-def test_random_command_soup_against_oracle():
+@pytest.mark.parametrize("fusion,seed", [(0, 2026), (1, 2026), (2, 2026), (2, 7), (2, 8), (2, 9)])
+def test_random_command_soup_against_oracle(fusion, seed):
     """Long random sequence of N / E-runs / M / 1q ops: exercises hole creation, hole filling,
-    tile shifts, extent trimming and the pending-scale bookkeeping together."""
-    rng = np.random.default_rng(2026)
+    tile shifts, extent trimming, the pending-scale bookkeeping and (fusion = 2) virtual qubits,
+    queued CZs absorbed by projections and the fused N,E,M butterfly together."""
+    rng = np.random.default_rng(seed)
     n0 = 13
     psi = rand_state(rng, n0)
-    dev, orc = _sv(psi, 16), OracleStatevector(psi, max_qubits=16)
-    for step in range(120):
+    dev, orc = _sv(psi, 16, fusion=fusion), OracleStatevector(psi, max_qubits=16)
+    for step in range(160):
         n = orc.nqubit
         kind = rng.choice(["N", "E", "M", "U", "Z"], p=[0.25, 0.3, 0.25, 0.1, 0.1])
         if kind == "N" and n < 16:
@@ -145,8 +148,9 @@ def test_random_command_soup_against_oracle():
             vec = rng.normal(size=3)
             vec /= np.linalg.norm(vec)
             pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
-            pd, po = dev.expectation_single(pm, q), orc.expectation_single(pm, q)
-            assert abs(pd - po) < 1e-10
+            if rng.integers(2):
+                pd, po = dev.expectation_single(pm, q), orc.expectation_single(pm, q)
+                assert abs(pd - po) < 1e-10
             dev.project_qubit(pm, q)
             orc.project_qubit(pm, q)
         elif kind == "U":
@@ -159,11 +163,52 @@ def test_random_command_soup_against_oracle():
             m = [mbqc.Ops.Z, mbqc.Ops.X, mbqc.Ops.S][int(rng.integers(3))]
             dev.evolve_single(m, q)
             orc.evolve_single(m, q)
-        if step % 10 == 9:
+        if step % 20 == 19:
             assert dev.nqubit == orc.nqubit
             np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
     np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
     assert abs(dev.norm2() - 1) < 1e-12
+
+
+def test_lazy_fusion_triples_and_virtual_qubits():
+    """fusion = 2: N and E are queued; M of a qubit with a virtual partner runs the fused butterfly
+    (the new qubit takes the measured qubit's physical bit, no hole, state never grows)."""
+    rng = np.random.default_rng(5)
+    n = 12
+    psi = rand_state(rng, n)
+    dev, orc = _sv(psi, n, fusion=2), OracleStatevector(psi, max_qubits=n + 3)
+    for step in range(40):
+        m = int(rng.integers(n))
+        others = [int(x) for x in rng.choice([i for i in range(n) if i != m], size=2, replace=False)]
+        st = [mbqc.BasicStates.PLUS, mbqc.PlanarState(mbqc.Plane.XY, 0.3), mbqc.BasicStates.ZERO][step % 3]
+        for s in (dev, orc):
+            s.add_nodes(1, st)                   # new qubit, logical index n
+            s.entangle((n, m))
+            s.entangle((m, others[0]))           # real-real edge on the measured qubit
+            if step % 2:
+                s.entangle((n, others[1]))       # real partner of the new qubit
+            if step % 5 == 0:
+                s.add_nodes(1, mbqc.BasicStates.PLUS)   # second virtual partner of m
+                s.entangle((n + 1, m))
+                s.entangle((n + 1, n))                  # virtual-virtual edge
+        assert dev.max_qubits <= n + 1           # virtual qubits occupy no memory
+        vec = rng.normal(size=3)
+        vec /= np.linalg.norm(vec)
+        pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
+        dev.project_qubit(pm, m)
+        orc.project_qubit(pm, m)
+        if step % 5 == 0:
+            # drop the extra qubit again so the width stays n
+            pm2 = outcome_to_operator_matrix((0.6, 0.0, 0.8), 0)
+            dev.project_qubit(pm2, n)
+            orc.project_qubit(pm2, n)
+        assert dev.nqubit == orc.nqubit == n
+        if step % 8 == 7:
+            np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
+    np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
+    st = dev.stats()
+    # CZs are only ever issued by the read-outs above (flatten flushes the queue), never per command
+    assert st["fused"]["launches"] >= 40 and st["cz"]["launches"] <= 6
 
 
 def test_measure_all_then_regrow():
