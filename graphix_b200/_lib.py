@@ -11,7 +11,7 @@ import os
 from . import _build
 
 GXSV_OK, GXSV_EINDEX, GXSV_EVALUE, GXSV_EZERONORM, GXSV_ECUDA, GXSV_ENOMEM, GXSV_EUNSUPPORTED = range(7)
-OPT_FUSION, OPT_STRICT, OPT_PROFILE = 1, 2, 3
+OPT_FUSION, OPT_STRICT, OPT_PROFILE, OPT_DIST = 1, 2, 3, 4
 KIND_NAMES = ("fill", "cz", "contract", "apply1q", "expect", "gather", "fused", "tensor", "misc")
 K_COUNT = len(KIND_NAMES)
 
@@ -60,6 +60,14 @@ SIGNATURES = {
     "gxsv_stats": (C.c_int, [_H, C.POINTER(Stats)]),
     "gxsv_reset_stats": (C.c_int, [_H]),
     "gxsv_layout": (C.c_int, [_H, _I]),
+    "gxsv_nreal": (C.c_int, [_H]),
+    "gxsv_is_virtual": (C.c_int, [_H, C.c_int]),
+    "gxsv_settle": (C.c_int, [_H, C.c_int]),
+    "gxsv_set_norm": (C.c_int, [_H, C.c_double]),
+    "gxsv_scale_host": (C.c_int, [_H, C.c_double, C.c_double]),
+    "gxsv_scale": (C.c_int, [_H, C.c_double, C.c_double]),
+    "gxsv_pack_half": (C.c_int, [_H, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "gxsv_unpack_half": (C.c_int, [_H, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_double, C.c_double]),
 }
 
 _lib = None

@@ -69,6 +69,7 @@ struct gxsv {
   int fusion = 1;
   int strict = 1;
   int profile = 0;
+  int dist = 0;            // sharded: projections publish local norms, the host sets g after the all-reduce
   int sm_count = 148;
   gxsv_stats_t stats;
   std::vector<ProfRec> prof;
@@ -346,6 +347,10 @@ int materialize(gxsv_t* h, int qi) {
     else
       k_fill<U_DEF, 1><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hb, d2(1.0), d2(f1), nlive);
     h->hscale *= s0;
+  } else if (h->dist) {
+    // sharded: s1 may carry a rank-dependent sign, so nothing of it may go to the (rank-uniform) host scalar
+    Launch L(h, GXSV_K_FILL, 3.0 * S);
+    k_fill<U_DEF, 2><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hb, d2(s0), d2(s1), nlive);
   } else {
     // |s0| small (e.g. |1>): defer s1 instead, lower half scaled by s0/s1
     const cplx f0 = s0 / s1;
@@ -419,7 +424,8 @@ int launch_contract(gxsv_t* h, int qidx, cplx c0, cplx c1, uint64_t mq, unsigned
     {
       Launch Lc(h, GXSV_K_CONTRACT, 1.5 * S);
       k_contract<U_DEF, false><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hs, p, d2(c0), d2(c1), mq, nout,
-                                                           h->partials, h->ctrl, slot, seq);
+                                                           h->partials, h->ctrl, slot, seq,
+                                                           h->dist ? FIN_CONTRACT_DIST : FIN_CONTRACT);
     }
     h->live_mask &= ~(1ull << p);
   } else {
@@ -434,7 +440,8 @@ int launch_contract(gxsv_t* h, int qidx, cplx c0, cplx c1, uint64_t mq, unsigned
     {
       Launch Lc(h, GXSV_K_CONTRACT, 1.5 * S);
       k_contract<U_DEF, true><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hd, p, d2(c0), d2(c1), mq, nout,
-                                                          h->partials, h->ctrl, slot, seq);
+                                                          h->partials, h->ctrl, slot, seq,
+                                                          h->dist ? FIN_CONTRACT_DIST : FIN_CONTRACT);
     }
     // qubits on L[t+1 .. K-1] slide down one live slot
     for (auto& qb : h->q) {
@@ -596,6 +603,7 @@ int gxsv_set_option(gxsv_t* h, int key, int value) {
       if (!value) prof_collect(h);
       h->profile = value ? 1 : 0;
       return GXSV_OK;
+    case GXSV_OPT_DIST: h->dist = value ? 1 : 0; return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -605,6 +613,7 @@ int gxsv_get_option(gxsv_t* h, int key, int* value) {
     case GXSV_OPT_FUSION: *value = h->fusion; return GXSV_OK;
     case GXSV_OPT_STRICT: *value = h->strict; return GXSV_OK;
     case GXSV_OPT_PROFILE: *value = h->profile; return GXSV_OK;
+    case GXSV_OPT_DIST: *value = h->dist; return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -883,7 +892,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           Launch L(h, GXSV_K_FUSED, 2.0 * state_bytes(h));
           k_fused<U_DEF><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(
               h->psi, hs, p, d2(s0 * c0), d2(s0 * c1), d2(s1 * c0), d2(-s1 * c1), mq, mv, npair, h->partials, h->ctrl,
-              slot, seq);
+              slot, seq, h->dist ? FIN_CONTRACT_DIST : FIN_CONTRACT);
         }
         rc = check_launch(h, "k_fused");
         if (rc) return rc;
@@ -894,6 +903,13 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     h->hscale = 1.0;
     if (!h->strict) {
       if (norms) { norms[0] = norms[1] = NAN; }
+      return GXSV_OK;
+    }
+    if (h->dist) {
+      // sharded: hand the LOCAL half-norms back; the caller all-reduces, checks and calls gxsv_set_norm
+      rc = wait_slot(h, seq, v);
+      if (rc) return rc;
+      if (norms) { norms[0] = v[0] * (r0 / rbig); norms[1] = v[0] * (r1 / rbig); }
       return GXSV_OK;
     }
     rc = wait_slot(h, seq, v);
@@ -916,6 +932,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     return GXSV_OK;
   }
   // general 2x2 (not a projector): literal two-pass reference algorithm
+  if (h->dist) return fail(h, GXSV_EUNSUPPORTED, "sharded states project rank-1 operators only");
   rc = settle(h, q);
   if (rc) return rc;
   const int p = h->q[q].phys;
@@ -1049,6 +1066,79 @@ int gxsv_fidelity(gxsv_t* a, gxsv_t* b, double* out) {
   cudaFree(xa);
   cudaFree(xb);
   return rc;
+}
+
+// ---- sharded-state plumbing ---------------------------------------------------
+int gxsv_nreal(gxsv_t* h) { return nlive_bits(h); }
+
+int gxsv_is_virtual(gxsv_t* h, int q) {
+  if (q < 0 || q >= (int)h->q.size()) return -1;
+  return h->q[q].phys < 0 ? 1 : 0;
+}
+
+int gxsv_settle(gxsv_t* h, int q) {
+  CU(cudaSetDevice(h->device));
+  int rc = check_q(h, q);
+  if (rc) return rc;
+  if (h->fusion < 2) return flush_pending(h);
+  return settle(h, q);
+}
+
+int gxsv_set_norm(gxsv_t* h, double total_norm2) {
+  CU(cudaSetDevice(h->device));
+  if (!(total_norm2 > 0.0)) return fail(h, GXSV_EZERONORM, "set_norm: non-positive norm");
+  const double g = 1.0 / std::sqrt(total_norm2);
+  CU(cudaMemcpyAsync(&h->ctrl->g, &g, sizeof g, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return GXSV_OK;
+}
+
+int gxsv_scale_host(gxsv_t* h, double re, double im) {
+  h->hscale *= cplx(re, im);
+  return GXSV_OK;
+}
+
+int gxsv_scale(gxsv_t* h, double re, double im) {
+  CU(cudaSetDevice(h->device));
+  const uint64_t nlive = 1ull << nlive_bits(h);
+  Holes hs = make_holes(h);
+  {
+    Launch L(h, GXSV_K_MISC, 2.0 * state_bytes(h));
+    k_scale_all<U_DEF><<<grid_for(h, nlive, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, make_double2(re, im), nlive);
+  }
+  return check_launch(h, "k_scale_all");
+}
+
+static int pack_common(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, void* buf, bool pack, double re,
+                       double im) {
+  CU(cudaSetDevice(h->device));
+  int rc = check_q(h, q);
+  if (rc) return rc;
+  if (h->q[q].phys < 0 || has_edge(h, h->q[q].id))
+    return fail(h, GXSV_EVALUE, "pack/unpack: qubit %d must be settled first", q);
+  const int p = h->q[q].phys;
+  const uint64_t half = 1ull << (nlive_bits(h) - 1);
+  if (first + count > half) return fail(h, GXSV_EVALUE, "pack/unpack: range exceeds the half shard");
+  Holes hs = make_holes(h, p);
+  const uint64_t pv = (uint64_t)(bitval ? 1 : 0) << p;
+  {
+    Launch L(h, GXSV_K_MISC, 32.0 * (double)count);
+    if (pack)
+      k_pack_half<U_DEF><<<grid_for(h, count, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, pv, first, count, (double2*)buf);
+    else
+      k_unpack_half<U_DEF><<<grid_for(h, count, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, pv, first, count,
+                                                                          (const double2*)buf, make_double2(re, im));
+  }
+  return check_launch(h, pack ? "k_pack_half" : "k_unpack_half");
+}
+
+int gxsv_pack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, void* out_device) {
+  return pack_common(h, q, bitval, first, count, out_device, true, 1.0, 0.0);
+}
+
+int gxsv_unpack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, const void* in_device,
+                     double re, double im) {
+  return pack_common(h, q, bitval, first, count, (void*)in_device, false, re, im);
 }
 
 int gxsv_sync(gxsv_t* h) {

@@ -97,13 +97,15 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* NV*8 
   }
 }
 
-enum { FIN_CONTRACT = 0, FIN_SCALED = 1 };
+enum { FIN_CONTRACT = 0, FIN_SCALED = 1, FIN_CONTRACT_DIST = 2 };
 
 // Writes the block partial, elects the last block, which sums all partials in a
 // fixed order and publishes the result to the host-mapped slot.
 //   FIN_CONTRACT: v[0] = sum |stored'|^2 (the stored state now has that norm);
 //                 ctrl->g = 1/sqrt(v[0]) so that g*stored is normalised.
 //   FIN_SCALED  : v[k] *= post * g^2 (expectation values / norms of the true state).
+//   FIN_CONTRACT_DIST: sharded state — publish the local sum only; g is set by the host after the
+//                 all-reduce over ranks (gxsv_set_norm).
 template <int NV>
 __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restrict__ partials, Ctrl* ctrl,
                                             Res* res, unsigned long long seq, int mode, double post, double g) {
@@ -132,6 +134,8 @@ __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restric
     ctrl->ticket = 0;
     if (mode == FIN_CONTRACT) {
       ctrl->g = 1.0 / sqrt(tot[0]);
+      res->v[0] = tot[0];
+    } else if (mode == FIN_CONTRACT_DIST) {
       res->v[0] = tot[0];
     } else {
 #pragma unroll
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(TPB) k_contract(double2* __restrict__ psi, con
                                                   const __grid_constant__ Holes hd, const int pbit, double2 c0,
                                                   double2 c1, const uint64_t mq, const uint64_t nout,
                                                   double* __restrict__ partials, Ctrl* ctrl, Res* res,
-                                                  const unsigned long long seq) {
+                                                  const unsigned long long seq, const int fin_mode) {
   const double g = ctrl->g;
   c0.x *= g; c0.y *= g; c1.x *= g; c1.y *= g;
   const uint64_t chunk = (uint64_t)TPB * U;
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(TPB) k_contract(double2* __restrict__ psi, con
       }
     }
   }
-  grid_finish<1>(acc, partials, ctrl, res, seq, FIN_CONTRACT, 1.0, g);
+  grid_finish<1>(acc, partials, ctrl, res, seq, fin_mode, 1.0, g);
 }
 
 // ---------------------------------------------------------------------------
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const 
                                                const int pbit, double2 m00, double2 m01, double2 m10, double2 m11,
                                                const uint64_t mq, const uint64_t mv, const uint64_t npair,
                                                double* __restrict__ partials, Ctrl* ctrl, Res* res,
-                                               const unsigned long long seq) {
+                                               const unsigned long long seq, const int fin_mode) {
   const double g = ctrl->g;
   m00.x *= g; m00.y *= g; m01.x *= g; m01.y *= g; m10.x *= g; m10.y *= g; m11.x *= g; m11.y *= g;
   const uint64_t chunk = (uint64_t)TPB * U;
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const 
       }
     }
   }
-  grid_finish<1>(acc, partials, ctrl, res, seq, FIN_CONTRACT, 1.0, g);
+  grid_finish<1>(acc, partials, ctrl, res, seq, fin_mode, 1.0, g);
 }
 
 // ---------------------------------------------------------------------------
@@ -524,6 +528,50 @@ __global__ void __launch_bounds__(TPB) k_gather(const double2* __restrict__ psi,
     const uint64_t p = st[0][i & 255] | st[1][(i >> 8) & 255] | st[2][(i >> 16) & 255] | st[3][(i >> 24) & 255] |
                        st[4][(i >> 32) & 255];
     out[k] = cmul(f, __ldg(psi + p));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Sharded states: the half of the live sub-cube with bit p = bitval, in dense rank order, is
+// packed into / unpacked from a contiguous staging buffer for the NVLink half-shard exchange
+// that swaps a global (rank-index) qubit with the local qubit on bit p.  `hs` = holes + {p}.
+// ---------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(TPB) k_pack_half(const double2* __restrict__ psi, const __grid_constant__ Holes hs,
+                                                   const uint64_t pbitval, const uint64_t first, const uint64_t count,
+                                                   double2* __restrict__ out) {
+  const uint64_t chunk = (uint64_t)TPB * U;
+  for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < count; base += (uint64_t)gridDim.x * chunk) {
+    double2 a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
+      if (k < count) a[u] = ld_amp(psi + (expand(first + k, hs) | pbitval));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
+      if (k < count) out[k] = a[u];
+    }
+  }
+}
+template <int U>
+__global__ void __launch_bounds__(TPB) k_unpack_half(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+                                                     const uint64_t pbitval, const uint64_t first, const uint64_t count,
+                                                     const double2* __restrict__ in, const double2 f) {
+  const uint64_t chunk = (uint64_t)TPB * U;
+  for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < count; base += (uint64_t)gridDim.x * chunk) {
+    double2 a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
+      if (k < count) a[u] = in[k];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
+      if (k < count) st_amp(psi + (expand(first + k, hs) | pbitval), cmul(f, a[u]));
+    }
   }
 }
 

@@ -1,0 +1,618 @@
+"""Statevector sharded over ranks by its top (rank-index) qubits — SURVEY.md §8(e).
+
+One process per GPU (``torchrun``); every rank walks the same command stream and takes the same
+branch.  Rank ``r`` holds the sub-cube of the amplitude index whose *global* bits equal the bits
+of ``r``; the remaining bits are the local engine's (``libgxsv`` in ``GXSV_OPT_DIST`` mode, lazy
+fusion on).  This module is host logic only — layout decisions, the exchange schedule and the
+collectives — and is engine-agnostic, so the same code runs under ``gloo`` on CPU with the
+test double of ``tests/cpu_shard_engine.py``.
+
+Rules
+* A global bit with no qubit on it is *replicated*: the ranks differing only in that bit hold the
+  same shard and do the same work, so putting a freshly prepared qubit on it costs **no
+  communication** (each rank scales by its own amplitude).  Qubits go to the local engine while it
+  has room (``local_bits``) and to global bits after that.
+* Commands on local qubits run on the shard with no communication.  CZ never communicates: between
+  two global qubits it is a per-rank sign, between a local and a global qubit it is a Z on the
+  ranks whose bit is 1 — queued and folded into the next projection of that local qubit.
+* Z / diagonal gates on a global qubit are per-rank scalars, X is a relabel of the rank bit.
+* Probabilities and norms: one small all-reduce.
+* A projection (or any non-diagonal 2x2) on a global qubit first swaps it with a local qubit: each
+  rank sends one half of its shard to the partner rank and receives the other half (NCCL
+  send/recv over NVLink, chunked through a bounded staging buffer).  Global bits therefore never
+  die, and every rank keeps an equal share of the state when qubits are removed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections.abc import Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .backend import B200StatevectorBackend, NodeIndex
+from .mbqc import BasicStates, RandomBranchSelector
+from .statevec import B200Statevector, NoiseNotSupportedError, _op8
+
+_Z = np.array([[1, 0], [0, -1]], dtype=np.complex128)
+_X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+
+
+class GpuShardEngine:
+    """The local shard: a ``B200Statevector`` in distributed mode plus torch staging buffers."""
+
+    def __init__(self, local_bits: int, device: int | None = None) -> None:
+        self.sv = B200Statevector(nqubit=0, max_qubits=local_bits, device=device, fusion=2, strict=True)
+        self.sv.set_option(_lib.OPT_DIST, 1)
+        self.capacity = local_bits
+        self.device = torch.device("cuda", self.sv._device)
+        self._lib = self.sv._lib
+        self._h = self.sv._h
+
+    # queries
+    @property
+    def nqubit(self) -> int:
+        return self.sv.nqubit
+
+    @property
+    def nreal(self) -> int:
+        return self._lib.gxsv_nreal(self._h)
+
+    def is_virtual(self, q: int) -> bool:
+        return self._lib.gxsv_is_virtual(self._h, q) == 1
+
+    def half_size(self) -> int:
+        return 1 << (self.nreal - 1)
+
+    # commands
+    def add_qubit(self, s0: complex, s1: complex) -> None:
+        self.sv._check(self._lib.gxsv_add_qubit(self._h, (C.c_double * 4)(s0.real, s0.imag, s1.real, s1.imag)))
+
+    def entangle(self, a: int, b: int) -> None:
+        self.sv.entangle((a, b))
+
+    def evolve_single(self, q: int, m) -> None:
+        self.sv.evolve_single(m, q)
+
+    def expectation_local(self, q: int, m) -> complex:
+        return self.sv.expectation_single(m, q)
+
+    def project_local(self, q: int, m) -> tuple[float, float]:
+        norms = (C.c_double * 2)()
+        self.sv._check(self._lib.gxsv_project_qubit(self._h, q, _op8(m), 0.0, norms))
+        return norms[0], norms[1]
+
+    def set_norm(self, total: float) -> None:
+        self.sv._check(self._lib.gxsv_set_norm(self._h, total))
+
+    def scale_host(self, c: complex) -> None:
+        self.sv._check(self._lib.gxsv_scale_host(self._h, c.real, c.imag))
+
+    def scale(self, c: complex) -> None:
+        self.sv._check(self._lib.gxsv_scale(self._h, c.real, c.imag))
+
+    def settle(self, q: int) -> None:
+        self.sv._check(self._lib.gxsv_settle(self._h, q))
+
+    def pack_half(self, q: int, bit: int, first: int, count: int, out: torch.Tensor) -> None:
+        self.sv._check(self._lib.gxsv_pack_half(self._h, q, bit, first, count, C.c_void_p(out.data_ptr())))
+
+    def unpack_half(self, q: int, bit: int, first: int, count: int, src: torch.Tensor, factor: complex) -> None:
+        self.sv._check(self._lib.gxsv_unpack_half(self._h, q, bit, first, count, C.c_void_p(src.data_ptr()),
+                                                  factor.real, factor.imag))
+
+    def norm2_local(self) -> float:
+        return self.sv.norm2()
+
+    def flatten_local(self) -> np.ndarray:
+        return self.sv.flatten()
+
+    def reset(self) -> None:
+        self.sv.reset()
+
+    def sync(self) -> None:
+        self.sv.sync()
+
+    def stats(self):
+        return self.sv.stats()
+
+    def reset_stats(self) -> None:
+        self.sv.reset_stats()
+
+    def set_option(self, key: int, value: int) -> None:
+        self.sv.set_option(key, value)
+
+
+class _Q:
+    """Location of one logical qubit: local engine index ``li`` or global bit ``g``."""
+
+    __slots__ = ("li", "g")
+
+    def __init__(self, li: int | None = None, g: int | None = None) -> None:
+        self.li = li
+        self.g = g
+
+
+class ShardedStatevector:
+    """State object with the reference ``Statevector`` surface over P ranks (P a power of two)."""
+
+    CHUNK = 1 << 24  # amplitudes per staging buffer (256 MiB)
+
+    def __init__(self, engine, group=None) -> None:
+        self.engine = engine
+        self.group = group
+        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.P & (self.P - 1):
+            raise ValueError("the number of ranks must be a power of two")
+        self.gbits = self.P.bit_length() - 1
+        self._stage: dict[str, torch.Tensor] = {}
+        self.exchanged_bytes = 0
+        self.n_swaps = 0
+        self._clear()
+
+    def _clear(self) -> None:
+        self.q: list[_Q] = []                      # logical order (reference convention: index 0 = MSB)
+        self.owner: list[_Q | None] = [None] * self.gbits   # qubit on each global bit (None = replicated)
+        self.flip = [0] * self.gbits               # logical value of a global qubit = rank bit ^ flip
+        self.u = np.ones(self.P, dtype=np.complex128)       # rank-dependent scalar of every rank's shard
+        self.pend_lg: list[tuple[_Q, _Q]] = []     # queued CZ(local, global)
+        self.pend_z: dict[int, int] = {}           # queued Z on local qubits (id(_Q) -> parity)
+
+    # -- helpers -----------------------------------------------------------------------
+    def _eb(self, k: int, r: int | None = None) -> int:
+        r = self.rank if r is None else r
+        return ((r >> k) & 1) ^ self.flip[k]
+
+    def _dead(self) -> int:
+        return sum(1 for o in self.owner if o is None)
+
+    def _allreduce(self, vals: Sequence[float]) -> list[float]:
+        if self.P == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.engine.device)
+        dist.all_reduce(t, group=self.group)
+        return t.tolist()
+
+    def _sigma(self, qb: _Q) -> int:
+        """Parity of the Z's queued on local qubit ``qb`` for this rank."""
+        s = self.pend_z.get(id(qb), 0)
+        for a, b in self.pend_lg:
+            if a is qb:
+                s ^= self._eb(b.g)
+        return s
+
+    def _drop_pending(self, qb: _Q) -> None:
+        self.pend_z.pop(id(qb), None)
+        self.pend_lg = [(a, b) for (a, b) in self.pend_lg if a is not qb]
+
+    def _flush_local(self, qb: _Q) -> None:
+        """Apply the queued Z's of local qubit ``qb`` for real."""
+        if self._sigma(qb):
+            self.engine.evolve_single(qb.li, _Z)
+        self._drop_pending(qb)
+
+    def _check(self, q: int) -> _Q:
+        if not 0 <= q < len(self.q):
+            raise IndexError(f"Qubit index {q} out of range [0, {len(self.q) - 1}]")
+        return self.q[q]
+
+    # -- reference surface ---------------------------------------------------------------
+    @property
+    def nqubit(self) -> int:
+        return len(self.q)
+
+    @property
+    def max_qubits(self) -> int:
+        return self.engine.capacity + self.gbits
+
+    def add_nodes(self, nqubit: int, data) -> None:
+        """statevec.py:269-300 (product states; a joint 2^k vector is only accepted for k = 1)."""
+        states = self._states_of(nqubit, data)
+        for s0, s1 in states:
+            if self.engine.nqubit < self.engine.capacity:
+                self.engine.add_qubit(s0, s1)
+                self.q.append(_Q(li=self.engine.nqubit - 1))
+                continue
+            free = [k for k in range(self.gbits) if self.owner[k] is None]
+            if not free:
+                raise MemoryError(f"sharded state is full: {self.max_qubits} qubits")
+            k = free[0]
+            # replicated bit becomes live: every rank keeps its copy and takes its own amplitude
+            qb = _Q(g=k)
+            self.owner[k] = qb
+            self.flip[k] = 0
+            mine = s1 if (self.rank >> k) & 1 else s0
+            if s0 == 0 or s1 == 0:
+                self.engine.scale(complex(mine))      # exact zeros cannot live in the bookkeeping scalar
+            else:
+                for r in range(self.P):
+                    self.u[r] *= s1 if (r >> k) & 1 else s0
+            self.q.append(qb)
+
+    @staticmethod
+    def _states_of(nqubit: int, data) -> list[tuple[complex, complex]]:
+        if hasattr(data, "to_statevector_numpy"):
+            v = np.asarray(data.to_statevector_numpy(), dtype=np.complex128)
+            return [(complex(v[0]), complex(v[1]))] * nqubit
+        items = list(data)
+        if items and hasattr(items[0], "to_statevector_numpy"):
+            if len(items) != nqubit:
+                raise ValueError(f"Mismatch between nqubit and length of input state: {nqubit} != {len(items)}.")
+            out = []
+            for s in items:
+                v = np.asarray(s.to_statevector_numpy(), dtype=np.complex128)
+                out.append((complex(v[0]), complex(v[1])))
+            return out
+        v = np.asarray(items, dtype=np.complex128)
+        if v.size == 2 and nqubit == 1:
+            if not np.isclose(np.linalg.norm(v), 1.0):
+                raise ValueError("Input state is not normalized.")
+            return [(complex(v[0]), complex(v[1]))]
+        raise NotImplementedError("sharded states accept product states (State objects) only")
+
+    def entangle(self, qubits: tuple[int, int]) -> None:
+        a, b = self._check(qubits[0]), self._check(qubits[1])
+        if a is b:
+            raise ValueError("entangle: control and target must differ")
+        if a.g is None and b.g is None:
+            self.engine.entangle(a.li, b.li)
+        elif a.g is not None and b.g is not None:
+            for r in range(self.P):
+                if self._eb(a.g, r) & self._eb(b.g, r):
+                    self.u[r] = -self.u[r]
+        else:
+            loc, glo = (a, b) if a.g is None else (b, a)
+            if self.engine.is_virtual(loc.li):
+                if self._eb(glo.g):
+                    self.engine.evolve_single(loc.li, _Z)   # host-side update of the prepared state: free
+            else:
+                self.pend_lg.append((loc, glo))
+
+    def evolve_single(self, op, qubit: int) -> None:
+        qb = self._check(qubit)
+        m = np.asarray(op, dtype=np.complex128)
+        diagonal = m[0, 1] == 0 and m[1, 0] == 0
+        if qb.g is not None:
+            k = qb.g
+            if diagonal:
+                for r in range(self.P):
+                    self.u[r] *= m[1, 1] if self._eb(k, r) else m[0, 0]
+                return
+            if m[0, 0] == 0 and m[1, 1] == 0:
+                # [[0, a], [b, 0]] = X . diag(b, a): per-rank scalar, then relabel the rank bit.
+                for r in range(self.P):
+                    self.u[r] *= m[0, 1] if self._eb(k, r) else m[1, 0]
+                # X_k CZ_{lk} = CZ_{lk} Z_l X_k for every CZ still queued on k
+                for a, b in self.pend_lg:
+                    if b is qb:
+                        self.pend_z[id(a)] = self.pend_z.get(id(a), 0) ^ 1
+                self.flip[k] ^= 1
+                return
+            if self.engine.nqubit == 0:
+                self._evolve_global_scalar(qb, m)
+                return
+            self._swap_in(qb)
+        if diagonal:
+            self.engine.evolve_single(qb.li, m)
+            return
+        self._flush_local(qb)
+        self.engine.evolve_single(qb.li, m)
+
+    def expectation_single(self, op, qubit: int) -> complex:
+        qb = self._check(qubit)
+        if qb.g is not None:
+            if self.engine.nqubit == 0:
+                return self._expect_global_scalar(qb, np.asarray(op, dtype=np.complex128))
+            self._swap_in(qb)
+        m = np.array(op, dtype=np.complex128)
+        if self._sigma(qb):
+            m[0, 1], m[1, 0] = -m[0, 1], -m[1, 0]     # Z op Z
+        loc = self.engine.expectation_local(qb.li, m)
+        w = abs(self.u[self.rank]) ** 2
+        re, im = self._allreduce([w * loc.real, w * loc.imag])
+        scale = 1.0 / (1 << self._dead())
+        return complex(re * scale, im * scale)
+
+    def project_qubit(self, op, qubit: int) -> None:
+        """statevec.py:430-495 for rank-1 ``op`` (the projectors ``measure`` builds)."""
+        qb = self._check(qubit)
+        if qb.g is not None:
+            if self.engine.nqubit == 0:
+                self._project_global_scalar(qb, np.asarray(op, dtype=np.complex128))
+                return
+            self._swap_in(qb)
+        m = np.array(op, dtype=np.complex128)
+        if self._sigma(qb):
+            m[0, 1], m[1, 1] = -m[0, 1], -m[1, 1]     # op . Z: the queued Z's act first
+        self._drop_pending(qb)
+        n0l, n1l = self.engine.project_local(qb.li, m)
+        w = abs(self.u[self.rank]) ** 2
+        n0, n1 = self._allreduce([w * n0l, w * n1l])
+        scale = 1.0 / (1 << self._dead())
+        n0, n1 = n0 * scale, n1 * scale
+        r0 = abs(m[0, 0]) ** 2 + abs(m[0, 1]) ** 2
+        r1 = abs(m[1, 0]) ** 2 + abs(m[1, 1]) ** 2
+        big = 0 if r0 >= r1 else 1
+        li = qb.li
+        self._remove(qb)
+        for o in self.q:
+            if o.li is not None and o.li > li:
+                o.li -= 1
+        pick = 0
+        if n0 <= 1e-10:
+            pick = 1
+            if n1 <= 1e-10:
+                raise RuntimeError(f"Attempted to remove qubit {qubit} from 0-norm statevector.")
+        self.engine.set_norm(n1 if big else n0)
+        if pick != big:
+            row_b, row_p = m[big], m[pick]
+            c = 0 if abs(row_b[0]) >= abs(row_b[1]) else 1
+            ratio = row_p[c] / row_b[c]
+            if abs(ratio) > 0:
+                self.engine.scale_host(complex(ratio / abs(ratio)))
+
+    def _remove(self, qb: _Q) -> None:
+        self.q = [o for o in self.q if o is not qb]
+
+    def _global_scalars(self) -> np.ndarray:
+        """Every remaining qubit is global: the shards are scalars; gather them (true amplitudes)."""
+        val = complex(self.engine.flatten_local()[0]) * self.u[self.rank]
+        re = self._allgather_scalar(val.real)
+        im = self._allgather_scalar(val.imag)
+        return np.array(re) + 1j * np.array(im)
+
+    def _evolve_global_scalar(self, qb: _Q, m: np.ndarray) -> None:
+        k = qb.g
+        vals = self._global_scalars()
+        out = np.zeros(self.P, dtype=np.complex128)
+        for r in range(self.P):
+            e = self._eb(k, r)
+            partner = r ^ (1 << k)
+            v = [0j, 0j]
+            v[e], v[1 - e] = vals[r], vals[partner]
+            out[r] = m[e, 0] * v[0] + m[e, 1] * v[1]
+        self.engine.reset()
+        self.u = out
+
+    def _expect_global_scalar(self, qb: _Q, m: np.ndarray) -> complex:
+        k = qb.g
+        vals = self._global_scalars()
+        tot = 0j
+        for r in range(self.P):
+            if (r >> k) & 1:
+                continue
+            lo, hi = r, r | (1 << k)
+            v = (vals[lo], vals[hi]) if self.flip[k] == 0 else (vals[hi], vals[lo])
+            for a in (0, 1):
+                for b in (0, 1):
+                    tot += np.conj(v[a]) * m[a, b] * v[b]
+        return complex(tot / (1 << self._dead()))
+
+    def _project_global_scalar(self, qb: _Q, m: np.ndarray) -> None:
+        """Edge case: every remaining qubit is global, the shards are scalars — contract on the host."""
+        k = qb.g
+        vals = self._global_scalars()
+        r0 = abs(m[0, 0]) ** 2 + abs(m[0, 1]) ** 2
+        r1 = abs(m[1, 0]) ** 2 + abs(m[1, 1]) ** 2
+        big = 0 if r0 >= r1 else 1
+        out = np.zeros(self.P, dtype=np.complex128)
+        for r in range(self.P):
+            lo = r & ~(1 << k)
+            hi = r | (1 << k)
+            v0, v1 = (vals[lo], vals[hi]) if self.flip[k] == 0 else (vals[hi], vals[lo])
+            out[r] = m[big, 0] * v0 + m[big, 1] * v1
+        self.owner[k] = None
+        self.flip[k] = 0
+        self._remove(qb)
+        nbig = float(np.sum(np.abs(out) ** 2)) / (1 << self._dead())
+        n0, n1 = (nbig, nbig * r1 / r0) if big == 0 else (nbig * r0 / r1, nbig)
+        if n0 <= 1e-10 and n1 <= 1e-10:
+            raise RuntimeError("Attempted to remove qubit from 0-norm statevector.")
+        pick = 0 if n0 > 1e-10 else 1
+        phase = 1.0
+        if pick != big:
+            c = 0 if abs(m[big, 0]) >= abs(m[big, 1]) else 1
+            ratio = m[pick, c] / m[big, c]
+            phase = ratio / abs(ratio) if abs(ratio) > 0 else 1.0
+        self.engine.reset()
+        self.u = out * phase / math.sqrt(nbig)
+        self.u[self.u == 0] = 0
+
+    def _allgather_scalar(self, x: float) -> list[float]:
+        t = torch.zeros(self.P, dtype=torch.float64, device=self.engine.device)
+        t[self.rank] = x
+        if self.P > 1:
+            dist.all_reduce(t, group=self.group)
+        return t.tolist()
+
+    # -- the exchange ------------------------------------------------------------------------
+    def _staging(self, name: str, count: int) -> torch.Tensor:
+        t = self._stage.get(name)
+        if t is None or t.numel() < count:
+            t = torch.empty(max(count, 1), dtype=torch.complex128, device=self.engine.device)
+            self._stage[name] = t
+        return t[:count]
+
+    def _pick_victim(self, exclude: _Q) -> _Q:
+        locals_ = [o for o in self.q if o.li is not None and o is not exclude]
+        if not locals_:
+            raise NotImplementedError("swap of a global qubit needs at least one local qubit")
+        real = [o for o in locals_ if not self.engine.is_virtual(o.li)]
+        pool = real if real else locals_
+        return max(pool, key=lambda o: o.li)       # the most recently added local qubit is measured last
+
+    def _swap_in(self, glo: _Q) -> None:
+        """Swap global qubit ``glo`` with a local qubit through a pairwise half-shard exchange."""
+        k = glo.g
+        vic = self._pick_victim(glo)
+        self._flush_local(vic)
+        self.engine.settle(vic.li)
+        B = (self.rank >> k) & 1
+        partner = self.rank ^ (1 << k)
+        half = self.engine.half_size()
+        factor = complex(self.u[partner] / self.u[self.rank]) if self.u[self.rank] != 0 else 1.0 + 0j
+        chunk = min(half, self.CHUNK)
+        for first in range(0, half, chunk):
+            count = min(chunk, half - first)
+            send = self._staging("send", count)
+            recv = self._staging("recv", count)
+            # my half with victim bit = 1-B goes to the partner, the partner's half with victim bit = B comes here
+            self.engine.pack_half(vic.li, 1 - B, first, count, send)
+            ops = [dist.P2POp(dist.isend, send, partner, group=self.group),
+                   dist.P2POp(dist.irecv, recv, partner, group=self.group)]
+            if self.rank > partner:
+                ops.reverse()
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            self.engine.unpack_half(vic.li, 1 - B, first, count, recv, factor)
+            self.exchanged_bytes += 16 * count
+        self.n_swaps += 1
+        # the victim's slot now carries `glo` with slot value = physical rank bit; undo a pending relabel
+        glo.li, glo.g = vic.li, None
+        vic.li, vic.g = None, k
+        self.owner[k] = vic
+        if self.flip[k]:
+            self.engine.evolve_single(glo.li, _X)
+            self.flip[k] = 0
+        # CZs queued between local qubits and `glo` are now local-local
+        keep = []
+        for a, b in self.pend_lg:
+            if b is glo:
+                self.engine.entangle(a.li, glo.li)
+            else:
+                keep.append((a, b))
+        self.pend_lg = keep
+
+    # -- relabels, read-out ---------------------------------------------------------------------
+    def swap(self, qubits: tuple[int, int]) -> None:
+        i, j = qubits
+        self._check(i), self._check(j)
+        self.q[i], self.q[j] = self.q[j], self.q[i]
+
+    def permute(self, permutation: Sequence[int]) -> None:
+        n = len(self.q)
+        if len(permutation) != n:
+            raise ValueError(f"Permutation has length {len(permutation)}, but {n} qubits expected.")
+        if set(permutation) != set(range(n)):
+            raise ValueError(f"{permutation} is not a permutation.")
+        self.q = [self.q[p] for p in permutation]
+
+    def norm2(self) -> float:
+        for o in self.q:
+            if o.li is not None:
+                self._flush_local(o)
+        w = abs(self.u[self.rank]) ** 2
+        (tot,) = self._allreduce([w * self.engine.norm2_local()])
+        return tot / (1 << self._dead())
+
+    def flatten(self) -> np.ndarray:
+        """Full state on every rank (read-out for tests / small widths): all-gather of the shards."""
+        n = len(self.q)
+        if n > 28:
+            raise MemoryError("flatten() of a sharded state is limited to 28 qubits")
+        for o in self.q:
+            if o.li is not None:
+                self._flush_local(o)
+        local = np.asarray(self.engine.flatten_local(), dtype=np.complex128) * self.u[self.rank]
+        nloc = self.engine.nqubit
+        if self.P > 1:
+            t = torch.from_numpy(np.ascontiguousarray(local).view(np.float64)).to(self.engine.device)
+            parts = [torch.empty_like(t) for _ in range(self.P)]
+            dist.all_gather(parts, t, group=self.group)
+            shards = [p.cpu().numpy().view(np.complex128) for p in parts]
+        else:
+            shards = [local]
+        full = np.zeros((2,) * n, dtype=np.complex128)
+        local_axes = [o.li for o in self.q if o.li is not None]     # engine axis of each local qubit, logical order
+        for r in range(self.P):
+            if any(self.owner[k] is None and (r >> k) & 1 for k in range(self.gbits)):
+                continue                                              # replica of a lower rank
+            idx = tuple(self._eb(o.g, r) if o.g is not None else slice(None) for o in self.q)
+            full[idx] = np.transpose(shards[r].reshape((2,) * nloc), local_axes) if nloc else shards[r][0]
+        return full.reshape(1 << n)
+
+    @property
+    def psi(self) -> np.ndarray:
+        return self.flatten()
+
+    def fidelity(self, other) -> float:
+        inner = np.dot(self.flatten().conjugate(), np.asarray(other.flatten()))
+        return float(np.abs(inner) ** 2)
+
+    def isclose(self, other, *, rtol: float = 1e-09, atol: float = 0.0) -> bool:
+        return math.isclose(self.fidelity(other), 1, rel_tol=rtol, abs_tol=atol)
+
+    def apply_noise(self, qubits, noise) -> None:  # noqa: ARG002
+        raise NoiseNotSupportedError
+
+    def reset(self) -> None:
+        self.engine.reset()
+        self._clear()
+
+    def sync(self) -> None:
+        self.engine.sync()
+
+    def stats(self):
+        return self.engine.stats()
+
+    def reset_stats(self) -> None:
+        self.engine.reset_stats()
+        self.exchanged_bytes = 0
+        self.n_swaps = 0
+
+    def set_option(self, key: int, value: int) -> None:
+        self.engine.set_option(key, value)
+
+    def layout(self) -> list[str]:
+        return [f"g{o.g}" if o.g is not None else f"l{o.li}" for o in self.q]
+
+
+class ShardedStatevectorBackend(B200StatevectorBackend):
+    """``Backend`` over a :class:`ShardedStatevector`; same contract as ``B200StatevectorBackend``."""
+
+    def __init__(self, state: ShardedStatevector, *, node_index=None, branch_selector=None, symbolic: bool = False) -> None:
+        if symbolic:
+            raise ValueError("Statevector backend does not support `symbolic` simulation.")
+        set_ = object.__setattr__
+        set_(self, "state", state)
+        set_(self, "node_index", NodeIndex() if node_index is None else node_index)
+        set_(self, "branch_selector", RandomBranchSelector() if branch_selector is None else branch_selector)
+        set_(self, "symbolic", False)
+
+    @classmethod
+    def with_capacity(cls, max_qubits: int, state=None, *, engine=None, group=None, device: int | None = None,
+                      fusion: int = 2, **kwargs) -> "ShardedStatevectorBackend":
+        """``max_qubits`` is the TOTAL width (``Pattern.max_space()``); each rank holds ``max_qubits - log2 P`` bits."""
+        del fusion, state
+        P = dist.get_world_size(group) if dist.is_initialized() else 1
+        g = P.bit_length() - 1
+        if engine is None:
+            engine = GpuShardEngine(max(max_qubits - g, 1), device=device)
+        return cls(ShardedStatevector(engine, group=group), **kwargs)
+
+    def measure(self, node: int, measurement, rng=None, *, stacklevel: int = 1):
+        """base_backend.py:812-856 through the generic state surface."""
+        loc = self.node_index.index(node)
+        bloch = measurement.to_bloch()
+        x, y, z = (float(v) for v in bloch.plane.polar(bloch.angle))
+
+        def proj(sign: float) -> np.ndarray:
+            return np.array([[0.5 + 0.5 * sign * z, 0.5 * sign * (x - 1j * y)],
+                             [0.5 * sign * (x + 1j * y), 0.5 - 0.5 * sign * z]], dtype=np.complex128)
+
+        def f_expectation0() -> float:
+            v = self.state.expectation_single(proj(1.0), loc)
+            assert abs(v.imag) <= 1e-10
+            return v.real
+
+        outcome = self.branch_selector.measure(node, f_expectation0, rng, stacklevel=stacklevel + 1)
+        self.state.project_qubit(proj(-1.0 if outcome else 1.0), loc)
+        self.node_index.remove(node)
+        return outcome
+
+
+__all__ = ["GpuShardEngine", "ShardedStatevector", "ShardedStatevectorBackend", "BasicStates"]

@@ -51,7 +51,8 @@ enum {
 enum {
   GXSV_OPT_FUSION = 1,  /* 0 = one kernel per command, 1 = fuse runs of E (default), 2 = lazy N/E->M fusion */
   GXSV_OPT_STRICT = 2,  /* 1 (default) = project_qubit waits for the norm and raises like the reference */
-  GXSV_OPT_PROFILE = 3  /* 1 = bracket every launch with CUDA events (gxsv_profile_read) */
+  GXSV_OPT_PROFILE = 3, /* 1 = bracket every launch with CUDA events (read back through gxsv_stats) */
+  GXSV_OPT_DIST = 4     /* 1 = this handle is one shard of a distributed state (see the sharded section) */
 };
 
 /* kernel kinds reported by gxsv_profile_read / gxsv_stats */
@@ -149,6 +150,23 @@ int gxsv_fidelity(gxsv_t* a, gxsv_t* b, double* out);
 int gxsv_norm2(gxsv_t* h, double* out);
 /* replace the state by 2^n host amplitudes in reference order (Statevector(data), statevec.py:93-216) */
 int gxsv_set_state(gxsv_t* h, int n, const double* vec_host);
+
+/* ---- sharded states (no counterpart in the single-process reference) ----
+ * With GXSV_OPT_DIST = 1 the handle holds the local sub-cube of a state sharded over ranks by its top
+ * (rank-index) qubits.  gxsv_project_qubit then returns the LOCAL half-norms and leaves the
+ * normalisation to gxsv_set_norm(total) after the caller's all-reduce; gxsv_expectation_single
+ * returns the local contribution.  pack/unpack move one half of the local sub-cube (bit of qubit q
+ * = bitval, dense order, elements [first, first+count)) to / from a contiguous device staging
+ * buffer for the half-shard exchange that swaps a rank-index qubit with local qubit q. */
+int gxsv_nreal(gxsv_t* h);                 /* materialised local qubits */
+int gxsv_is_virtual(gxsv_t* h, int q);     /* 1 = prepared but not materialised (lazy mode) */
+int gxsv_settle(gxsv_t* h, int q);         /* materialise q and issue every queued CZ touching it */
+int gxsv_set_norm(gxsv_t* h, double total_norm2);
+int gxsv_scale_host(gxsv_t* h, double re, double im); /* multiply the pending host scalar (no pass) */
+int gxsv_scale(gxsv_t* h, double re, double im);      /* multiply every local amplitude (one pass) */
+int gxsv_pack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, void* out_device);
+int gxsv_unpack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, const void* in_device,
+                     double re, double im);
 
 /* ---- plumbing -------------------------------------------------------- */
 
