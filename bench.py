@@ -9,7 +9,8 @@ N/E/M/X/Z/C command, finalize) of the workload under ``ConstBranchSelector(0)``.
 * N = 1 : BASELINE config 2, ``rand_circuit(26, 20)`` space-minimised pattern, 3756 commands, 26<->27 live
   qubits, complex128 (state 1-2 GiB, far larger than the 126 MB L2, so no flush is needed between steps).
 * N > 1 : (torchrun, one rank per GPU) the state is sharded by its top log2(N) qubits
-  (``graphix_b200.sharded``); weak scaling: the QFT pattern grows by one qubit per doubling of N.
+  (``graphix_b200.sharded``); weak scaling: ``rand_circuit(26 + log2 N, 20)``, i.e. the per-GPU shard stays
+  1-2 GiB, every command touches N times more amplitudes, and ideal scaling keeps commands/s constant.
 
 Prints ONE JSON line (rank 0).  ``value`` = commands/s with the inputs resident in HBM, timed with CUDA events
 on the launching stream (max over ranks); ``e2e`` = the same through the public call with HOST buffers (the
@@ -52,11 +53,10 @@ def measured_peak() -> tuple[float, str]:
 def workload_for(n_gpus: int, name: str | None) -> str:
     if name:
         return name
-    if n_gpus == 1:
-        return "config2_rand26x20"
-    # weak scaling anchor: 29 + log2(N) circuit qubits (30.. live) so that every N fits any B200 pool quickly;
-    # the 33..36-live-qubit series of BASELINE config 4 is selected with --workload config4_qft32.. (128 GiB/GPU)
-    return {2: "config4_qft29", 4: "config4_qft29", 8: "config4_qft29"}.get(n_gpus, "config4_qft29")
+    # weak scaling of the N = 1 workload: one more circuit qubit per doubling of the GPU count, so every GPU
+    # keeps a 1-2 GiB shard.  The 33..36-live-qubit series of BASELINE config 4 (64-128 GiB per GPU) is selected
+    # with --workload config4_qft32 / 33 / 34 / 35 (use --max-commands for a bounded prefix window).
+    return {1: "config2_rand26x20", 2: "scale_rand27x20", 4: "scale_rand28x20", 8: "scale_rand29x20"}[n_gpus]
 
 
 class ClockSampler:
@@ -222,8 +222,11 @@ def gpu_arm(args) -> None:
 
     name = workload_for(args.gpus, args.workload)
     pattern = load_pattern(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
-    ncmd = len(pattern)
     width = pattern.max_space()
+    if args.max_commands:
+        # bounded prefix window: the first --max-commands commands; whatever is alive then is the output
+        pattern = mbqc.Pattern(pattern.input_nodes, list(pattern)[: args.max_commands])
+    ncmd = len(pattern)
     selector = mbqc.ConstBranchSelector(0)
 
     if world > 1:
@@ -273,6 +276,38 @@ def gpu_arm(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     value = ncmd * args.steps / (dev_ms * 1e-3)
+
+    # ---- secondary: the per-command kernels (fusion = 1), same pattern, same timing rules ----------
+    per_command = None
+    if world == 1 and args.fusion == 2 and not args.no_per_command:
+        b1 = B200StatevectorBackend.with_capacity(width, branch_selector=selector, fusion=1, device=local_rank)
+
+        def step1() -> None:
+            b1.state.reset()
+            b1.node_index.clear()
+            PatternSimulator(pattern, b1).run()
+
+        for _ in range(max(1, args.warmup - 1)):
+            step1()
+        b1.state.reset_stats()
+        b1.state.set_option(_lib.OPT_PROFILE, 1)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step1()
+        e1.record()
+        barrier()
+        ms1 = e0.elapsed_time(e1)
+        st1 = {k: v for k, v in b1.state.stats().items() if v["launches"]}
+        peak1, _ = measured_peak()
+        per_command = {
+            "fusion": 1, "value": ncmd * args.steps / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1 / args.steps,
+            "kernels": {k: {"launches_per_step": v["launches"] / args.steps, "ms_per_launch": v["device_ms"] / v["launches"],
+                            "GBps": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9,
+                            "frac_of_measured_peak": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9 / peak1}
+                        for k, v in st1.items() if v["device_ms"] > 0},
+        }
+        del b1
 
     # ---- end-to-end arm: host input vector in, host final state out ------------
     e2e = None
@@ -334,7 +369,7 @@ def gpu_arm(args) -> None:
     cpu_baseline = None
     if world == 1 and not args.no_cpu and width <= 31:
         cores = os.cpu_count() or 1
-        n_cmds = args.cpu_window or max(3, min(30, int(round(12 * 2.0 ** (27 - width)))) if width >= 24 else 300)
+        n_cmds = args.cpu_window or (max(6, min(240, int(round(60 * 2.0 ** (27 - width))))) if width >= 22 else 600)
         times = cpu_window(pattern, n_cmds, 1, 0)
         if times:
             cpu_baseline = {"value": n_cmds / times[0], "unit": UNIT, "cores": cores, "kind": "port",
@@ -347,11 +382,17 @@ def gpu_arm(args) -> None:
         "dtype": "c128", "data": "synthetic",
         "config": {"workload": name, "commands_per_step": ncmd, "live_qubits": f"{width - 1}<->{width}",
                    "state_bytes_max": 16 << (width if world == 1 else width), "selector": "ConstBranchSelector(0)",
-                   "fusion": args.fusion, "parallelism": f"shard{world}" if world > 1 else "single",
+                   "fusion": args.fusion, "max_commands": args.max_commands or None,
+                   "parallelism": f"shard{world}" if world > 1 else "single",
                    "l2": "state >> 126 MB L2: inputs larger than L2, no flush needed"},
         "e2e": e2e, "gpu_launches": int(sum(v["launches"] for v in kinds.values())),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": per_kind,
+        "per_command": per_command,
     }
+    if world > 1:
+        st = backend.state
+        line["exchange"] = {"swaps_per_step": st.n_swaps / args.steps,
+                            "nvlink_bytes_per_rank_per_step": st.exchanged_bytes / args.steps}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -364,7 +405,10 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, help="pattern fixture name under tests/golden/patterns")
-    ap.add_argument("--fusion", type=int, default=1)
+    ap.add_argument("--fusion", type=int, default=2,
+                    help="2 = lazy N/E->M fusion (default), 1 = one kernel per command with runs of E fused, 0 = none")
+    ap.add_argument("--max-commands", type=int, default=0, help="simulate only the first K commands of the pattern")
+    ap.add_argument("--no-per-command", action="store_true", help="skip the secondary fusion=1 measurement")
     ap.add_argument("--cpu-window", type=int, default=0, help="commands per CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -350,6 +350,10 @@ def gen_bench_patterns() -> None:
     for n in (29, 32, 33, 34, 35):
         p = pipeline(qft_circuit(n))
         emit(f"config4_qft{n}", p, [], meta={"generator": f"qft_circuit({n}) pipeline"})
+    # weak-scaling series of the N = 1 workload: one more circuit qubit per doubling of the GPU count
+    for w in (27, 28, 29):
+        p = pipeline(rand_circuit(w, 20, rng=np.random.default_rng(42)))
+        emit(f"scale_rand{w}x20", p, [], meta={"generator": f"rand_circuit({w}, 20, rng=default_rng(42)) pipeline"})
     # mid-size cases whose reference run is still feasible on host cores (used by the CPU baseline leg)
     p = pipeline(rand_circuit(20, 5, rng=np.random.default_rng(42)))
     emit("rand20x5", p, [], meta={"generator": "rand_circuit(20, 5, rng=default_rng(42)) pipeline"})
