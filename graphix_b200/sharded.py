@@ -14,7 +14,8 @@ Rules
   has room (``local_bits``) and to global bits after that.
 * Commands on local qubits run on the shard with no communication.  CZ never communicates: between
   two global qubits it is a per-rank sign, between a local and a global qubit it is a Z on the
-  ranks whose bit is 1 — queued and folded into the next projection of that local qubit.
+  ranks whose bit is 1 — queued and folded into the next projection of that local qubit (or turned
+  back into a local CZ if the global qubit is swapped into the shard first).
 * Z / diagonal gates on a global qubit are per-rank scalars, X is a relabel of the rank bit.
 * Probabilities and norms: one small all-reduce.
 * A projection (or any non-diagonal 2x2) on a global qubit first swaps it with a local qubit: each
@@ -266,11 +267,9 @@ class ShardedStatevector:
                     self.u[r] = -self.u[r]
         else:
             loc, glo = (a, b) if a.g is None else (b, a)
-            if self.engine.is_virtual(loc.li):
-                if self._eb(glo.g):
-                    self.engine.evolve_single(loc.li, _Z)   # host-side update of the prepared state: free
-            else:
-                self.pend_lg.append((loc, glo))
+            # Z on `loc` for the ranks whose bit of `glo` is 1.  Always queued: it is folded into the next
+            # projection of `loc` for free, and it must follow `glo` if that qubit is swapped into the shard.
+            self.pend_lg.append((loc, glo))
 
     def evolve_single(self, op, qubit: int) -> None:
         qb = self._check(qubit)
@@ -431,11 +430,12 @@ class ShardedStatevector:
 
     # -- the exchange ------------------------------------------------------------------------
     def _staging(self, name: str, count: int) -> torch.Tensor:
+        """``count`` amplitudes as 2*count float64 (NCCL has no complex types: (re, im) pairs travel as doubles)."""
         t = self._stage.get(name)
-        if t is None or t.numel() < count:
-            t = torch.empty(max(count, 1), dtype=torch.complex128, device=self.engine.device)
+        if t is None or t.numel() < 2 * count:
+            t = torch.empty(max(2 * count, 2), dtype=torch.float64, device=self.engine.device)
             self._stage[name] = t
-        return t[:count]
+        return t[: 2 * count]
 
     def _pick_victim(self, exclude: _Q) -> _Q:
         locals_ = [o for o in self.q if o.li is not None and o is not exclude]

@@ -1,10 +1,10 @@
 """numpy stand-in for the local shard engine (``graphix_b200.sharded.GpuShardEngine``).
 
 TEST DOUBLE ONLY: lets the host-side sharding logic of ``graphix_b200/sharded.py`` (layout decisions,
-exchange schedule, collectives) run under ``gloo`` on CPU with world_size > 1.  It keeps the same
-contract as the CUDA engine: projections return LOCAL half-norms and leave the state unnormalised
-until ``set_norm(total)``; freshly added qubits stay virtual until something other than a diagonal
-gate touches the engine.
+exchange schedule, collectives) run under ``gloo`` on CPU with world_size > 1.  It keeps the contract
+of the CUDA engine in distributed mode, including its laziness: a prepared qubit stays *virtual*
+(a 2-vector plus queued CZs) until a non-diagonal operation touches it or one of its CZ partners;
+projections return LOCAL half-norms and leave the state unnormalised until ``set_norm(total)``.
 """
 from __future__ import annotations
 
@@ -19,113 +19,147 @@ class CpuShardEngine:
         self.reset()
 
     def reset(self) -> None:
-        self.psi = np.array([1], dtype=np.complex128)   # canonical order over materialised local qubits
-        self.n_real = 0
-        self.virt: list[list[complex]] = []             # trailing virtual qubits
+        self.ids: list[int] = []                 # logical order -> stable id
+        self.virt: dict[int, list[complex]] = {}  # id -> prepared state while virtual
+        self.real: list[int] = []                # ids of materialised qubits = axes of self.t, in order
+        self.t = np.ones((), dtype=np.complex128)
+        self.pend: list[tuple[int, int]] = []    # queued CZs (ids), at least one endpoint virtual
+        self._next = 0
 
     # -- queries
     @property
     def nqubit(self) -> int:
-        return self.n_real + len(self.virt)
+        return len(self.ids)
 
     @property
     def nreal(self) -> int:
-        return self.n_real
+        return len(self.real)
 
     def is_virtual(self, q: int) -> bool:
-        return q >= self.n_real
+        return self.ids[q] in self.virt
 
     def half_size(self) -> int:
-        return 1 << (self.n_real - 1)
+        return 1 << (len(self.real) - 1)
 
-    def _materialise(self) -> None:
-        for s0, s1 in self.virt:
-            self.psi = np.kron(self.psi, np.array([s0, s1], dtype=np.complex128))
-            self.n_real += 1
-        self.virt = []
+    # -- laziness
+    def _materialise(self, i: int) -> None:
+        if i not in self.virt:
+            return
+        s = np.array(self.virt.pop(i), dtype=np.complex128)
+        self.t = np.multiply.outer(self.t, s)
+        self.real.append(i)
+        keep = []
+        for a, b in self.pend:
+            if a not in self.virt and b not in self.virt:
+                self._cz(a, b)
+            else:
+                keep.append((a, b))
+        self.pend = keep
 
-    def _t(self) -> np.ndarray:
-        return self.psi.reshape((2,) * self.n_real)
+    def _cz(self, a: int, b: int) -> None:
+        idx = [slice(None)] * len(self.real)
+        idx[self.real.index(a)], idx[self.real.index(b)] = 1, 1
+        self.t[tuple(idx)] *= -1
+
+    def _settle_id(self, i: int) -> None:
+        self._materialise(i)
+        for a, b in list(self.pend):
+            if a == i or b == i:
+                self._materialise(b if a == i else a)
+
+    def _all(self) -> None:
+        for i in list(self.ids):
+            self._materialise(i)
+
+    def _axis(self, q: int) -> int:
+        return self.real.index(self.ids[q])
 
     # -- commands
     def add_qubit(self, s0: complex, s1: complex) -> None:
         assert self.nqubit < self.capacity
-        self.virt.append([s0, s1])
+        self.ids.append(self._next)
+        self.virt[self._next] = [s0, s1]
+        self._next += 1
 
     def entangle(self, a: int, b: int) -> None:
-        self._materialise()
-        t = self._t()
-        idx = [slice(None)] * self.n_real
-        idx[a], idx[b] = 1, 1
-        t[tuple(idx)] *= -1
+        ia, ib = self.ids[a], self.ids[b]
+        if ia in self.virt or ib in self.virt:
+            self.pend.append((ia, ib))
+        else:
+            self._cz(ia, ib)
 
     def evolve_single(self, q: int, m) -> None:
         m = np.asarray(m, dtype=np.complex128)
-        if q >= self.n_real and m[0, 1] == 0 and m[1, 0] == 0:
-            s = self.virt[q - self.n_real]
-            s[0], s[1] = m[0, 0] * s[0], m[1, 1] * s[1]
+        i = self.ids[q]
+        diagonal = m[0, 1] == 0 and m[1, 0] == 0
+        if i in self.virt and (diagonal or not any(i in e for e in self.pend)):
+            s = self.virt[i]
+            s[0], s[1] = m[0, 0] * s[0] + m[0, 1] * s[1], m[1, 0] * s[0] + m[1, 1] * s[1]
             return
-        self._materialise()
-        t = np.moveaxis(self._t(), q, 0)
-        new = np.tensordot(m, t, axes=(1, 0))
-        self.psi = np.ascontiguousarray(np.moveaxis(new, 0, q)).reshape(-1)
+        if i in self.virt or not diagonal:
+            self._settle_id(i)
+        ax = self._axis(q)
+        self.t = np.moveaxis(np.tensordot(m, np.moveaxis(self.t, ax, 0), axes=(1, 0)), 0, ax)
 
     def expectation_local(self, q: int, m) -> complex:
-        self._materialise()
+        self._settle_id(self.ids[q])
         m = np.asarray(m, dtype=np.complex128)
-        t = np.moveaxis(self._t(), q, 0)
-        new = np.tensordot(m, t, axes=(1, 0))
-        return complex(np.vdot(t, new))
+        t = np.moveaxis(self.t, self._axis(q), 0)
+        return complex(np.vdot(t, np.tensordot(m, t, axes=(1, 0))))
 
     def project_local(self, q: int, m) -> tuple[float, float]:
-        self._materialise()
+        i = self.ids[q]
+        self._settle_id(i)
         m = np.asarray(m, dtype=np.complex128)
-        t = np.moveaxis(self._t(), q, 0)
-        rows = np.tensordot(m, t, axes=(1, 0))
+        ax = self._axis(q)
+        rows = np.tensordot(m, np.moveaxis(self.t, ax, 0), axes=(1, 0))
         n0 = float(np.vdot(rows[0], rows[0]).real)
         n1 = float(np.vdot(rows[1], rows[1]).real)
         r0 = abs(m[0, 0]) ** 2 + abs(m[0, 1]) ** 2
         r1 = abs(m[1, 0]) ** 2 + abs(m[1, 1]) ** 2
-        big = 0 if r0 >= r1 else 1
-        self.psi = np.ascontiguousarray(rows[big]).reshape(-1)
-        self.n_real -= 1
+        self.t = np.array(rows[0 if r0 >= r1 else 1], dtype=np.complex128)  # keeps 0-d for the scalar state
+        self.real.remove(i)
+        self.ids.remove(i)
         return n0, n1
 
     def set_norm(self, total: float) -> None:
-        self.psi = self.psi / np.sqrt(total)
+        self.t = np.asarray(self.t / np.sqrt(total))
 
     def scale_host(self, c: complex) -> None:
-        self.psi = self.psi * c
+        self.t = np.asarray(self.t * c)
 
     def scale(self, c: complex) -> None:
-        self._materialise()
-        self.psi = self.psi * c
+        self.t = np.asarray(self.t * c)
 
     def settle(self, q: int) -> None:
-        self._materialise()
+        self._settle_id(self.ids[q])
 
     def _half_view(self, q: int, bit: int) -> np.ndarray:
-        return self.psi.reshape(1 << q, 2, 1 << (self.n_real - 1 - q))[:, bit, :]
+        ax = self._axis(q)
+        self.t = np.array(self.t, dtype=np.complex128, order="C")
+        n = len(self.real)
+        return self.t.reshape(1 << ax, 2, 1 << (n - 1 - ax))[:, bit, :]
 
     def pack_half(self, q: int, bit: int, first: int, count: int, out: torch.Tensor) -> None:
-        self._materialise()
+        i = self.ids[q]
+        assert i not in self.virt and not any(i in e for e in self.pend), "qubit must be settled first"
         flat = np.ascontiguousarray(self._half_view(q, bit)).reshape(-1)
-        out.numpy()[:count] = flat[first:first + count]
+        out.numpy().view(np.complex128)[:count] = flat[first:first + count]
 
     def unpack_half(self, q: int, bit: int, first: int, count: int, src: torch.Tensor, factor: complex) -> None:
-        self.psi = np.ascontiguousarray(self.psi)
         view = self._half_view(q, bit)
         flat = np.ascontiguousarray(view).reshape(-1)
-        flat[first:first + count] = src.numpy()[:count] * factor
+        flat[first:first + count] = src.numpy().view(np.complex128)[:count] * factor
         view[...] = flat.reshape(view.shape)
 
     def norm2_local(self) -> float:
-        self._materialise()
-        return float(np.vdot(self.psi, self.psi).real)
+        self._all()
+        return float(np.vdot(self.t, self.t).real)
 
     def flatten_local(self) -> np.ndarray:
-        self._materialise()
-        return self.psi.copy()
+        self._all()
+        order = [self.real.index(i) for i in self.ids]
+        return np.ascontiguousarray(np.transpose(self.t, order)).reshape(-1)
 
     def sync(self) -> None:
         pass
