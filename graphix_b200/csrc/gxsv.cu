@@ -835,17 +835,18 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     // op = u w^T: row r = u_r * w.  Contract with the larger row (best conditioned); the two half-norms the
     // reference computes (statevec.py:1185) differ from it only by the known factor |u_r|^2/|u_big|^2.
     const int big = (r0 >= r1) ? 0 : 1;
-    const cplx c0 = (big ? m10 : m00) * h->hscale, c1 = (big ? m11 : m01) * h->hscale;
     const double rbig = big ? r1 : r0;
+    // materialising queued qubits moves their amplitude s0 into the host scalar: settle first, read hscale after
+    if (h->fusion < 2) rc = flush_pending(h);
+    else if (h->q[q].phys < 0) rc = settle(h, q);
+    if (rc) return rc;
+    cplx c0 = (big ? m10 : m00) * h->hscale, c1 = (big ? m11 : m01) * h->hscale;
     if (h->fusion < 2) {
-      rc = flush_pending(h);
-      if (rc) return rc;
       rc = launch_contract(h, q, c0, c1, 0ull, &seq);
       if (rc) return rc;
     } else {
       // lazy mode: the CZs queued on q are applied inside the projection pass, and one virtual
       // partner of q is materialised by the same pass (k_fused)
-      if (h->q[q].phys < 0) { rc = settle(h, q); if (rc) return rc; }
       dedupe_pending(h);
       const int qid = h->q[q].id;
       std::vector<int> virt;  // logical indices of virtual partners
@@ -860,6 +861,8 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
         vi = virt.back();
         virt.pop_back();
         for (int i : virt) { rc = materialize(h, i); if (rc) return rc; }
+        c0 = (big ? m10 : m00) * h->hscale;
+        c1 = (big ? m11 : m01) * h->hscale;
       }
       const int vid = (vi >= 0) ? h->q[vi].id : -1;
       uint64_t mq = 0, mv = 0;

@@ -157,6 +157,22 @@ def case_vs_single_gpu(rank, world):
 CASES = {"golden": case_golden, "soup": case_soup, "vs_single": case_vs_single_gpu}
 
 
+def test_sharded_single_rank_runs_the_distributed_engine_mode():
+    """world_size 1 (no process group): the sharded state object drives libgxsv in GXSV_OPT_DIST mode
+    (local norms + set_norm, settle, lazy engine) on one GPU; golden traces and the soup must still match."""
+    from helpers import check_trace, load_golden
+
+    from graphix_b200.sharded import ShardedStatevectorBackend
+
+    for name in ("config1_rand8x5", "micro_prob", "handbuilt_allkinds", "qaoa7", "rand11x6"):
+        d = load_golden(name)
+        for trace in d["traces"]:
+            if trace["input"]["kind"] == "vector":
+                continue
+            check_trace(d, trace, lambda cap, sel: ShardedStatevectorBackend.with_capacity(cap, branch_selector=sel, device=0))
+    assert case_soup(0, 1) == 0
+
+
 def _need(world: int) -> None:
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")

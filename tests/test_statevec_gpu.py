@@ -211,6 +211,65 @@ def test_lazy_fusion_triples_and_virtual_qubits():
     assert st["fused"]["launches"] >= 40 and st["cz"]["launches"] <= 6
 
 
+@pytest.mark.parametrize("fusion", [0, 1, 2])
+def test_small_register_soup_down_to_zero_qubits(fusion):
+    """Registers of 0-4 qubits: gates on freshly prepared (still virtual) qubits, measuring the last qubit
+    (scalar state, phase included).  Regression: a virtual qubit whose amplitude s0 is complex (Y|+>) used
+    to lose that phase when it was measured before being materialised."""
+    st = mbqc.PlanarState(mbqc.Plane.YZ, 0.37)
+    rng = np.random.default_rng(0)
+    for trial in range(24):
+        vec = rng.normal(size=3)
+        vec /= np.linalg.norm(vec)
+        pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
+        first = [mbqc.BasicStates.PLUS, st, mbqc.BasicStates.MINUS][trial % 3]
+        res = []
+        for s in (OracleStatevector(nqubit=0, max_qubits=4), B200Statevector(nqubit=0, max_qubits=4, fusion=fusion)):
+            s.add_nodes(1, first)
+            if trial & 1:
+                s.evolve_single([mbqc.Ops.Y, mbqc.Clifford(17).matrix][(trial >> 3) & 1], 0)
+            if trial & 2:
+                s.add_nodes(1, st)
+                if trial & 4:
+                    s.entangle((0, 1))
+                    s.evolve_single(mbqc.Ops.S, 1)
+                s.project_qubit(outcome_to_operator_matrix((0.6, 0, 0.8), 0), 1)
+            s.project_qubit(pm, 0)
+            assert s.nqubit == 0
+            res.append(complex(s.flatten()[0]))
+        assert abs(res[0] - res[1]) < 1e-12, (trial, res)
+    rng = np.random.default_rng(501)
+    dev, orc = B200Statevector(nqubit=0, max_qubits=6, fusion=fusion), OracleStatevector(nqubit=0, max_qubits=6)
+    states = [mbqc.BasicStates.PLUS, mbqc.BasicStates.MINUS, mbqc.BasicStates.ZERO, mbqc.BasicStates.ONE, st]
+    for step in range(400):
+        n = orc.nqubit
+        kind = rng.choice(["N", "E", "M", "U", "D"], p=[0.3, 0.3, 0.24, 0.08, 0.08])
+        if kind == "N" and n < 6:
+            s_ = states[int(rng.integers(len(states)))]
+            dev.add_nodes(1, s_)
+            orc.add_nodes(1, s_)
+        elif kind == "E" and n >= 2:
+            a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+            dev.entangle((a, b))
+            orc.entangle((a, b))
+        elif kind == "M" and n >= 1:
+            q = int(rng.integers(n))
+            vec = rng.normal(size=3)
+            vec /= np.linalg.norm(vec)
+            pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
+            if orc.expectation_single(pm, q).real > 1e-6:
+                dev.project_qubit(pm, q)
+                orc.project_qubit(pm, q)
+        elif kind in ("U", "D") and n >= 1:
+            q = int(rng.integers(n))
+            m = mbqc.Clifford(int(rng.integers(24))).matrix if kind == "U" else \
+                [mbqc.Ops.Z, mbqc.Ops.X, mbqc.Ops.S, mbqc.Ops.Y][int(rng.integers(4))]
+            dev.evolve_single(m, q)
+            orc.evolve_single(m, q)
+        if step % 25 == 24:
+            np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11, err_msg=f"step {step}")
+
+
 def test_measure_all_then_regrow():
     """Shrink to 0 qubits (scalar state) and grow again; capacity growth without with_capacity."""
     sv = B200Statevector(nqubit=3, data=mbqc.BasicStates.PLUS)
