@@ -233,7 +233,9 @@ def gpu_arm(args) -> None:
         from graphix_b200.sharded import ShardedStatevectorBackend
 
         def make_backend():
-            return ShardedStatevectorBackend.with_capacity(width, branch_selector=selector, fusion=args.fusion)
+            # non-blocking projections: norms are all-reduced on the stream, the zero-norm check is deferred to finalize
+            return ShardedStatevectorBackend.with_capacity(width, branch_selector=selector, fusion=args.fusion,
+                                                           strict=not args.nonstrict)
     else:
         def make_backend():
             return B200StatevectorBackend.with_capacity(width, branch_selector=selector, fusion=args.fusion,
@@ -383,6 +385,7 @@ def gpu_arm(args) -> None:
         "config": {"workload": name, "commands_per_step": ncmd, "live_qubits": f"{width - 1}<->{width}",
                    "state_bytes_max": 16 << (width if world == 1 else width), "selector": "ConstBranchSelector(0)",
                    "fusion": args.fusion, "max_commands": args.max_commands or None,
+                   "strict_norm_check": True if world == 1 else (not args.nonstrict),
                    "parallelism": f"shard{world}" if world > 1 else "single",
                    "l2": "state >> 126 MB L2: inputs larger than L2, no flush needed"},
         "e2e": e2e, "gpu_launches": int(sum(v["launches"] for v in kinds.values())),
@@ -409,6 +412,9 @@ def main() -> None:
                     help="2 = lazy N/E->M fusion (default), 1 = one kernel per command with runs of E fused, 0 = none")
     ap.add_argument("--max-commands", type=int, default=0, help="simulate only the first K commands of the pattern")
     ap.add_argument("--no-per-command", action="store_true", help="skip the secondary fusion=1 measurement")
+    ap.add_argument("--strict", dest="nonstrict", action="store_false",
+                    help="N > 1: wait for the all-reduced norm of every projection (default: deferred check at finalize)")
+    ap.set_defaults(nonstrict=True)
     ap.add_argument("--cpu-window", type=int, default=0, help="commands per CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -69,6 +69,7 @@ struct gxsv {
   int fusion = 1;
   int strict = 1;
   int profile = 0;
+  double* sink = nullptr;  // device slot for local norms (sharded, see gxsv_set_norm_sink)
   int dist = 0;            // sharded: projections publish local norms, the host sets g after the all-reduce
   int sm_count = 148;
   gxsv_stats_t stats;
@@ -584,7 +585,8 @@ int gxsv_reset(gxsv_t* h) {
   h->live_mask = 0;
   h->hscale = 1.0;
   const double2 one = make_double2(1.0, 0.0);
-  const Ctrl c0 = {1.0, 0u, 0u};
+  Ctrl c0 = {1.0, 0u, 0u, nullptr};
+  c0.sink = h->sink;
   CU(cudaMemcpyAsync(h->psi, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->ctrl, &c0, sizeof c0, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -670,6 +672,7 @@ int gxsv_tensor(gxsv_t* h, int k, const double* vec) {
     h->hscale *= cplx(s0.x, s0.y) * c.g;
     c.g = 1.0;
     c.ticket = 0;
+    c.sink = h->sink;
     CU(cudaMemcpyAsync(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->psi, vec, sizeof(double2) * nnew, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -904,12 +907,15 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
       }
     }
     h->hscale = 1.0;
-    if (!h->strict) {
+    if (!h->strict && !h->dist) {
       if (norms) { norms[0] = norms[1] = NAN; }
       return GXSV_OK;
     }
     if (h->dist) {
-      // sharded: hand the LOCAL half-norms back; the caller all-reduces, checks and calls gxsv_set_norm
+      // sharded: hand the LOCAL half-norms back; the caller all-reduces, checks and calls gxsv_set_norm.
+      // Non-strict: nothing is waited for — the local norm^2 lands in the device sink, the caller all-reduces it
+      // on the stream and calls gxsv_set_norm_device.
+      if (!h->strict) { if (norms) { norms[0] = norms[1] = NAN; } return GXSV_OK; }
       rc = wait_slot(h, seq, v);
       if (rc) return rc;
       if (norms) { norms[0] = v[0] * (r0 / rbig); norms[1] = v[0] * (r1 / rbig); }
@@ -1094,6 +1100,21 @@ int gxsv_set_norm(gxsv_t* h, double total_norm2) {
   CU(cudaMemcpyAsync(&h->ctrl->g, &g, sizeof g, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return GXSV_OK;
+}
+
+int gxsv_set_norm_sink(gxsv_t* h, void* device_double) {
+  CU(cudaSetDevice(h->device));
+  h->sink = (double*)device_double;
+  CU(cudaMemcpyAsync(&h->ctrl->sink, &h->sink, sizeof(double*), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return GXSV_OK;
+}
+
+int gxsv_set_norm_device(gxsv_t* h, const void* device_total, double scale) {
+  CU(cudaSetDevice(h->device));
+  k_set_g<<<1, 1, 0, h->stream>>>(h->ctrl, (const double*)device_total, scale);
+  h->stats.launches[GXSV_K_MISC] += 1;
+  return check_launch(h, "k_set_g");
 }
 
 int gxsv_scale_host(gxsv_t* h, double re, double im) {

@@ -45,13 +45,17 @@ _X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
 class GpuShardEngine:
     """The local shard: a ``B200Statevector`` in distributed mode plus torch staging buffers."""
 
-    def __init__(self, local_bits: int, device: int | None = None) -> None:
-        self.sv = B200Statevector(nqubit=0, max_qubits=local_bits, device=device, fusion=2, strict=True)
+    def __init__(self, local_bits: int, device: int | None = None, strict: bool = True) -> None:
+        self.sv = B200Statevector(nqubit=0, max_qubits=local_bits, device=device, fusion=2, strict=strict)
         self.sv.set_option(_lib.OPT_DIST, 1)
         self.capacity = local_bits
         self.device = torch.device("cuda", self.sv._device)
         self._lib = self.sv._lib
         self._h = self.sv._h
+        self.strict = strict
+        # device slot the projection kernels drop their local norm^2 into (non-blocking path)
+        self.norm_buf = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self.sv._check(self._lib.gxsv_set_norm_sink(self._h, C.c_void_p(self.norm_buf.data_ptr())))
 
     # queries
     @property
@@ -88,6 +92,15 @@ class GpuShardEngine:
 
     def set_norm(self, total: float) -> None:
         self.sv._check(self._lib.gxsv_set_norm(self._h, total))
+
+    def project_local_async(self, q: int, m) -> torch.Tensor:
+        """Launch the projection without waiting; returns the device tensor that will hold the local norm^2
+        of the contracted row (valid in stream order)."""
+        self.sv._check(self._lib.gxsv_project_qubit(self._h, q, _op8(m), 0.0, None))
+        return self.norm_buf[:1]
+
+    def set_norm_device(self, total: torch.Tensor, scale: float) -> None:
+        self.sv._check(self._lib.gxsv_set_norm_device(self._h, C.c_void_p(total.data_ptr()), scale))
 
     def scale_host(self, c: complex) -> None:
         self.sv._check(self._lib.gxsv_scale_host(self._h, c.real, c.imag))
@@ -141,10 +154,16 @@ class ShardedStatevector:
     """State object with the reference ``Statevector`` surface over P ranks (P a power of two)."""
 
     CHUNK = 1 << 24  # amplitudes per staging buffer (256 MiB)
+    RING = 8192      # pinned slots for norms awaiting their deferred check (non-strict mode)
 
-    def __init__(self, engine, group=None) -> None:
+    def __init__(self, engine, group=None, strict: bool | None = None) -> None:
         self.engine = engine
         self.group = group
+        # strict: every projection waits for the all-reduced norm (zero-norm RuntimeError raised by the call
+        # itself, like the reference).  Non-strict: nothing waits; norms are checked at the next sync point.
+        self.strict = getattr(engine, "strict", True) if strict is None else strict
+        self._deferred: list[tuple[torch.Tensor, float, int]] = []
+        self._ring: torch.Tensor | None = None
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if self.P & (self.P - 1):
@@ -328,15 +347,41 @@ class ShardedStatevector:
         if self._sigma(qb):
             m[0, 1], m[1, 1] = -m[0, 1], -m[1, 1]     # op . Z: the queued Z's act first
         self._drop_pending(qb)
-        n0l, n1l = self.engine.project_local(qb.li, m)
-        w = abs(self.u[self.rank]) ** 2
-        n0, n1 = self._allreduce([w * n0l, w * n1l])
-        scale = 1.0 / (1 << self._dead())
-        n0, n1 = n0 * scale, n1 * scale
         r0 = abs(m[0, 0]) ** 2 + abs(m[0, 1]) ** 2
         r1 = abs(m[1, 0]) ** 2 + abs(m[1, 1]) ** 2
         big = 0 if r0 >= r1 else 1
+        w = abs(self.u[self.rank]) ** 2
+        scale = 1.0 / (1 << self._dead())
         li = qb.li
+        if not self.strict:
+            # non-blocking: local norm^2 -> on-stream all-reduce -> g set on the stream; host never waits
+            t = self.engine.project_local_async(li, m)
+            if w != 1.0:
+                t.mul_(w)
+            if self.P > 1:
+                dist.all_reduce(t, group=self.group)
+            self.engine.set_norm_device(t, scale)
+            if self._ring is None:
+                self._ring = torch.empty(self.RING, dtype=torch.float64, device="cpu", pin_memory=t.is_cuda)
+            if len(self._deferred) >= self.RING:
+                self.check_deferred()
+            keep = self._ring[len(self._deferred):len(self._deferred) + 1]
+            keep.copy_(t, non_blocking=True)
+            self._deferred.append((keep, scale * (r0 + r1) / (r1 if big else r0), qubit))
+            self._remove(qb)
+            for o in self.q:
+                if o.li is not None and o.li > li:
+                    o.li -= 1
+            if big == 1 and r0 > 1e-10 * r1:
+                # the reference keeps half 0 whenever its norm is above the cut-off: same phase convention
+                c = 0 if abs(m[1, 0]) >= abs(m[1, 1]) else 1
+                ratio = m[0, c] / m[1, c]
+                if abs(ratio) > 0:
+                    self.engine.scale_host(complex(ratio / abs(ratio)))
+            return
+        n0l, n1l = self.engine.project_local(li, m)
+        n0, n1 = self._allreduce([w * n0l, w * n1l])
+        n0, n1 = n0 * scale, n1 * scale
         self._remove(qb)
         for o in self.q:
             if o.li is not None and o.li > li:
@@ -502,6 +547,7 @@ class ShardedStatevector:
         self.q = [self.q[p] for p in permutation]
 
     def norm2(self) -> float:
+        self.check_deferred()
         for o in self.q:
             if o.li is not None:
                 self._flush_local(o)
@@ -514,6 +560,7 @@ class ShardedStatevector:
         n = len(self.q)
         if n > 28:
             raise MemoryError("flatten() of a sharded state is limited to 28 qubits")
+        self.check_deferred()
         for o in self.q:
             if o.li is not None:
                 self._flush_local(o)
@@ -550,11 +597,23 @@ class ShardedStatevector:
         raise NoiseNotSupportedError
 
     def reset(self) -> None:
+        self.check_deferred()
         self.engine.reset()
         self._clear()
 
+    def check_deferred(self) -> None:
+        """Non-strict mode: wait for the stream and raise the zero-norm RuntimeError of any past projection."""
+        if not self._deferred:
+            return
+        self.engine.sync()
+        pending, self._deferred = self._deferred, []
+        for keep, factor, qubit in pending:
+            if float(keep[0]) * factor <= 1e-10:
+                raise RuntimeError(f"Attempted to remove qubit {qubit} from 0-norm statevector (detected at sync).")
+
     def sync(self) -> None:
         self.engine.sync()
+        self.check_deferred()
 
     def stats(self):
         return self.engine.stats()
@@ -585,14 +644,14 @@ class ShardedStatevectorBackend(B200StatevectorBackend):
 
     @classmethod
     def with_capacity(cls, max_qubits: int, state=None, *, engine=None, group=None, device: int | None = None,
-                      fusion: int = 2, **kwargs) -> "ShardedStatevectorBackend":
+                      fusion: int = 2, strict: bool = True, **kwargs) -> "ShardedStatevectorBackend":
         """``max_qubits`` is the TOTAL width (``Pattern.max_space()``); each rank holds ``max_qubits - log2 P`` bits."""
         del fusion, state
         P = dist.get_world_size(group) if dist.is_initialized() else 1
         g = P.bit_length() - 1
         if engine is None:
-            engine = GpuShardEngine(max(max_qubits - g, 1), device=device)
-        return cls(ShardedStatevector(engine, group=group), **kwargs)
+            engine = GpuShardEngine(max(max_qubits - g, 1), device=device, strict=strict)
+        return cls(ShardedStatevector(engine, group=group, strict=strict), **kwargs)
 
     def measure(self, node: int, measurement, rng=None, *, stacklevel: int = 1):
         """base_backend.py:812-856 through the generic state surface."""
@@ -613,6 +672,10 @@ class ShardedStatevectorBackend(B200StatevectorBackend):
         self.state.project_qubit(proj(-1.0 if outcome else 1.0), loc)
         self.node_index.remove(node)
         return outcome
+
+    def finalize(self, output_nodes: Sequence[int]) -> None:
+        super().finalize(output_nodes)
+        self.state.check_deferred()
 
 
 __all__ = ["GpuShardEngine", "ShardedStatevector", "ShardedStatevectorBackend", "BasicStates"]
