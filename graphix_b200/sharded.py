@@ -153,7 +153,7 @@ class _Q:
 class ShardedStatevector:
     """State object with the reference ``Statevector`` surface over P ranks (P a power of two)."""
 
-    CHUNK = 1 << 24  # amplitudes per staging buffer (256 MiB)
+    CHUNK = 1 << 22  # amplitudes per staging buffer (64 MiB); two send + two receive buffers
     RING = 8192      # pinned slots for norms awaiting their deferred check (non-strict mode)
 
     def __init__(self, engine, group=None, strict: bool | None = None) -> None:
@@ -501,20 +501,30 @@ class ShardedStatevector:
         half = self.engine.half_size()
         factor = complex(self.u[partner] / self.u[self.rank]) if self.u[self.rank] != 0 else 1.0 + 0j
         chunk = min(half, self.CHUNK)
-        for first in range(0, half, chunk):
+        # software pipeline over chunks with two staging pairs: the NVLink transfer of chunk c overlaps with
+        # packing chunk c+1 and unpacking chunk c-1 (pack/unpack run on the compute stream, NCCL on its own)
+        inflight: list[tuple[list, int, int, torch.Tensor]] = []
+        for i, first in enumerate(range(0, half, chunk)):
             count = min(chunk, half - first)
-            send = self._staging("send", count)
-            recv = self._staging("recv", count)
+            send = self._staging(f"send{i & 1}", count)
+            recv = self._staging(f"recv{i & 1}", count)
             # my half with victim bit = 1-B goes to the partner, the partner's half with victim bit = B comes here
             self.engine.pack_half(vic.li, 1 - B, first, count, send)
             ops = [dist.P2POp(dist.isend, send, partner, group=self.group),
                    dist.P2POp(dist.irecv, recv, partner, group=self.group)]
             if self.rank > partner:
                 ops.reverse()
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-            self.engine.unpack_half(vic.li, 1 - B, first, count, recv, factor)
+            inflight.append((dist.batch_isend_irecv(ops), first, count, recv))
+            if len(inflight) == 2:
+                reqs, f0, c0, r0_ = inflight.pop(0)
+                for req in reqs:
+                    req.wait()
+                self.engine.unpack_half(vic.li, 1 - B, f0, c0, r0_, factor)
             self.exchanged_bytes += 16 * count
+        for reqs, f0, c0, r0_ in inflight:
+            for req in reqs:
+                req.wait()
+            self.engine.unpack_half(vic.li, 1 - B, f0, c0, r0_, factor)
         self.n_swaps += 1
         # the victim's slot now carries `glo` with slot value = physical rank bit; undo a pending relabel
         glo.li, glo.g = vic.li, None

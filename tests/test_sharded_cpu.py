@@ -105,6 +105,8 @@ def case_soup(rank, world):
         rng = np.random.default_rng(1000 + seed)
         cap = 7
         sh = ShardedStatevector(CpuShardEngine(cap - g))
+        if seed % 2 == 0:
+            sh.CHUNK = 4            # several chunks per exchange: exercises the double-buffered pipeline
         orc = OracleStatevector(nqubit=0, max_qubits=cap)
         states = [mbqc.BasicStates.PLUS, mbqc.BasicStates.MINUS, mbqc.BasicStates.ZERO, mbqc.BasicStates.ONE,
                   mbqc.PlanarState(mbqc.Plane.YZ, 0.37), mbqc.PlanarState(mbqc.Plane.XY, 1.21)]
