@@ -259,16 +259,30 @@ def gpu_arm(args) -> None:
     barrier()
     backend.state.reset_stats()
     backend.state.set_option(_lib.OPT_PROFILE, 1)
+    if world > 1:
+        backend.state.profile = True
+    host_t0 = time.perf_counter()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = None
+    if args.cprofile and rank == 0:
+        import cProfile
+
+        prof = cProfile.Profile()
+        prof.enable()
     barrier()
     e0.record()
     for _ in range(args.steps):
         one_step()
     e1.record()
     barrier()
+    if prof is not None:
+        import pstats
+
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(35)
     clocks = sampler.stop() if rank == 0 else {}
     dev_ms = e0.elapsed_time(e1)
     stats = backend.state.stats()
@@ -394,8 +408,13 @@ def gpu_arm(args) -> None:
     }
     if world > 1:
         st = backend.state
+        st.collect_profile()
         line["exchange"] = {"swaps_per_step": st.n_swaps / args.steps,
-                            "nvlink_bytes_per_rank_per_step": st.exchanged_bytes / args.steps}
+                            "nvlink_bytes_per_rank_per_step": st.exchanged_bytes / args.steps,
+                            "device_ms_per_step": st.exchange_ms / args.steps,
+                            "host_ms_per_step": st.exchange_host_ms / args.steps,
+                            "host_wait_for_device_ms_per_step": st.sync_wait_ms / args.steps,
+                            "GBps_per_direction": (st.exchanged_bytes / 1e9) / (st.exchange_ms * 1e-3) if st.exchange_ms else None}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -412,6 +431,7 @@ def main() -> None:
                     help="2 = lazy N/E->M fusion (default), 1 = one kernel per command with runs of E fused, 0 = none")
     ap.add_argument("--max-commands", type=int, default=0, help="simulate only the first K commands of the pattern")
     ap.add_argument("--no-per-command", action="store_true", help="skip the secondary fusion=1 measurement")
+    ap.add_argument("--cprofile", action="store_true", help="host-side cProfile of the timed region (rank 0, stderr)")
     ap.add_argument("--strict", dest="nonstrict", action="store_false",
                     help="N > 1: wait for the all-reduced norm of every projection (default: deferred check at finalize)")
     ap.set_defaults(nonstrict=True)

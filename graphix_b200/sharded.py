@@ -153,7 +153,8 @@ class _Q:
 class ShardedStatevector:
     """State object with the reference ``Statevector`` surface over P ranks (P a power of two)."""
 
-    CHUNK = 1 << 22  # amplitudes per staging buffer (64 MiB); two send + two receive buffers
+    CHUNK = 1 << 25  # amplitudes per staging buffer (512 MiB); two send + two receive buffers, allocated on demand.
+    # Large on purpose: one torch.distributed batch_isend_irecv costs ~0.3 ms of host time, a 512 MiB chunk ~0.7 ms of NVLink
     RING = 8192      # pinned slots for norms awaiting their deferred check (non-strict mode)
 
     def __init__(self, engine, group=None, strict: bool | None = None) -> None:
@@ -172,6 +173,11 @@ class ShardedStatevector:
         self._stage: dict[str, torch.Tensor] = {}
         self.exchanged_bytes = 0
         self.n_swaps = 0
+        self.profile = False            # bracket every exchange with CUDA events (bench.py)
+        self._xev: list[tuple] = []
+        self.exchange_ms = 0.0
+        self.exchange_host_ms = 0.0
+        self.sync_wait_ms = 0.0         # host time spent waiting for the device at deferred-check points
         self._clear()
 
     def _clear(self) -> None:
@@ -492,6 +498,26 @@ class ShardedStatevector:
 
     def _swap_in(self, glo: _Q) -> None:
         """Swap global qubit ``glo`` with a local qubit through a pairwise half-shard exchange."""
+        if self.profile and self.engine.device.type == "cuda":
+            import time  # noqa: PLC0415
+
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._swap_in_impl(glo)
+            e1.record()
+            self._xev.append((e0, e1))
+            self.exchange_host_ms += (time.perf_counter() - t0) * 1e3
+            return
+        self._swap_in_impl(glo)
+
+    def collect_profile(self) -> None:
+        if self._xev:
+            torch.cuda.synchronize()
+            self.exchange_ms += sum(a.elapsed_time(b) for a, b in self._xev)
+            self._xev = []
+
+    def _swap_in_impl(self, glo: _Q) -> None:
         k = glo.g
         vic = self._pick_victim(glo)
         self._flush_local(vic)
@@ -615,7 +641,11 @@ class ShardedStatevector:
         """Non-strict mode: wait for the stream and raise the zero-norm RuntimeError of any past projection."""
         if not self._deferred:
             return
+        import time  # noqa: PLC0415
+
+        t0 = time.perf_counter()
         self.engine.sync()
+        self.sync_wait_ms += (time.perf_counter() - t0) * 1e3
         pending, self._deferred = self._deferred, []
         for keep, factor, qubit in pending:
             if float(keep[0]) * factor <= 1e-10:
@@ -632,6 +662,10 @@ class ShardedStatevector:
         self.engine.reset_stats()
         self.exchanged_bytes = 0
         self.n_swaps = 0
+        self._xev = []
+        self.exchange_ms = 0.0
+        self.exchange_host_ms = 0.0
+        self.sync_wait_ms = 0.0
 
     def set_option(self, key: int, value: int) -> None:
         self.engine.set_option(key, value)
