@@ -60,6 +60,7 @@ SIGNATURES = {
     "gxsv_stats": (C.c_int, [_H, C.POINTER(Stats)]),
     "gxsv_reset_stats": (C.c_int, [_H]),
     "gxsv_layout": (C.c_int, [_H, _I]),
+    "gxsv_dm_trace_expect": (C.c_int, [_H, C.c_int, _I, _I, C.c_int, _D, _D]),
     "gxsv_nreal": (C.c_int, [_H]),
     "gxsv_is_virtual": (C.c_int, [_H, C.c_int]),
     "gxsv_settle": (C.c_int, [_H, C.c_int]),

@@ -791,8 +791,51 @@ int gxsv_swap(gxsv_t* h, int q1, int q2) {
 }
 
 int gxsv_evolve(gxsv_t* h, int k, const int* qubits, const double* op) {
-  (void)k; (void)qubits; (void)op;
-  return fail(h, GXSV_EUNSUPPORTED, "k-qubit evolve is not part of the pattern path (statevec.py:375-377)");
+  CU(cudaSetDevice(h->device));
+  if (k < 1 || k > 4) return fail(h, GXSV_EUNSUPPORTED, "evolve: operators on %d qubits are not supported (1..4)", k);
+  for (int i = 0; i < k; ++i) {
+    int rc = check_q(h, qubits[i]);
+    if (rc) return rc;
+    for (int j = 0; j < i; ++j)
+      if (qubits[i] == qubits[j]) return fail(h, GXSV_EVALUE, "evolve: repeated qubit %d", qubits[i]);
+  }
+  if (k == 1) return gxsv_evolve_single(h, qubits[0], op);
+  for (int i = 0; i < k; ++i) {
+    int rc = settle(h, qubits[i]);
+    if (rc) return rc;
+  }
+  const int n = nlive_bits(h);
+  const int D = 1 << k;
+  // operator index bit (k-1-i) <-> qubits[i]  (op reshaped (2,)*2k with the first k legs in `qubits` order)
+  GroupOffsets go;
+  for (int b = 0; b < D; ++b) {
+    uint64_t off = 0;
+    for (int i = 0; i < k; ++i)
+      if ((b >> (k - 1 - i)) & 1) off |= 1ull << h->q[qubits[i]].phys;
+    go.off[b] = off;
+  }
+  Holes hs;
+  hs.n = 0;
+  for (int b = 0; b < h->phys_bits; ++b) {
+    bool skip = !((h->live_mask >> b) & 1ull);
+    for (int i = 0; i < k; ++i) skip = skip || (h->q[qubits[i]].phys == b);
+    if (skip) hs.pos[hs.n++] = (unsigned char)b;
+  }
+  double2* dop = nullptr;
+  CU(cudaMalloc(&dop, sizeof(double2) * D * D));
+  CU(cudaMemcpyAsync(dop, op, sizeof(double2) * D * D, cudaMemcpyHostToDevice, h->stream));
+  const uint64_t ngroups = 1ull << (n - k);
+  const int grid = grid_for(h, ngroups, 1);
+  {
+    Launch L(h, GXSV_K_APPLY1Q, 2.0 * state_bytes(h));
+    if (k == 2) k_evolve<2><<<grid, TPB, 0, h->stream>>>(h->psi, hs, go, dop, ngroups);
+    else if (k == 3) k_evolve<3><<<grid, TPB, 0, h->stream>>>(h->psi, hs, go, dop, ngroups);
+    else k_evolve<4><<<grid, TPB, 0, h->stream>>>(h->psi, hs, go, dop, ngroups);
+  }
+  int rc = check_launch(h, "k_evolve");
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(dop));
+  return rc;
 }
 
 int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) {
@@ -1075,6 +1118,63 @@ int gxsv_fidelity(gxsv_t* a, gxsv_t* b, double* out) {
   cudaFree(xa);
   cudaFree(xb);
   return rc;
+}
+
+// ---- density matrices: rho vectorised over (row qubit, column qubit) pairs -----------------------
+int gxsv_dm_trace_expect(gxsv_t* h, int npairs, const int* rows, const int* cols, int target, const double m[8],
+                         double out[4]) {
+  CU(cudaSetDevice(h->device));
+  if (2 * npairs != (int)h->q.size()) return fail(h, GXSV_EVALUE, "dm: %d pairs do not cover %d qubits", npairs, (int)h->q.size());
+  if (target >= npairs) return fail(h, GXSV_EINDEX, "dm: target pair %d out of range", target);
+  for (int i = 0; i < npairs; ++i) {
+    int rc = check_q(h, rows[i]);
+    if (rc) return rc;
+    rc = check_q(h, cols[i]);
+    if (rc) return rc;
+  }
+  int rc = flush_pending(h);
+  if (rc) return rc;
+  static thread_local GatherTables t;
+  memset(&t, 0, sizeof t);
+  int nbits = 0;
+  uint64_t bitoff[64];
+  for (int i = 0; i < npairs; ++i) {
+    if (i == target) continue;
+    bitoff[nbits++] = (1ull << h->q[rows[i]].phys) | (1ull << h->q[cols[i]].phys);
+  }
+  for (int byte = 0; byte < 5; ++byte)
+    for (int v = 0; v < 256; ++v) {
+      uint64_t p = 0;
+      for (int b = 0; b < 8; ++b)
+        if (((v >> b) & 1) && byte * 8 + b < nbits) p |= bitoff[byte * 8 + b];
+      t.t[byte][v] = p;
+    }
+  CU(cudaMemcpyAsync(h->tabs_dev, &t, sizeof t, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const uint64_t nx = 1ull << nbits;
+  uint64_t roff = 0, coff = 0;
+  double2 z = make_double2(0.0, 0.0);
+  double2 m00 = z, m01 = z, m10 = z, m11 = z;
+  if (target >= 0) {
+    roff = 1ull << h->q[rows[target]].phys;
+    coff = 1ull << h->q[cols[target]].phys;
+    m00 = make_double2(m[0], m[1]); m01 = make_double2(m[2], m[3]);
+    m10 = make_double2(m[4], m[5]); m11 = make_double2(m[6], m[7]);
+  }
+  unsigned long long seq;
+  Res* slot = next_slot(h, &seq);
+  {
+    Launch L(h, GXSV_K_EXPECT, 16.0 * (double)nx * (target >= 0 ? 4.0 : 1.0));
+    k_dm_diag<<<grid_for(h, nx, 1), TPB, 0, h->stream>>>(h->psi, h->tabs_dev, nx, target >= 0 ? 1 : 0, roff, coff, m00,
+                                                         m01, m10, m11, h->partials, h->ctrl, slot, seq);
+  }
+  rc = check_launch(h, "k_dm_diag");
+  if (rc) return rc;
+  double v[4];
+  rc = wait_slot(h, seq, v);
+  if (rc) return rc;
+  for (int i = 0; i < 4; ++i) out[i] = v[i];
+  return GXSV_OK;
 }
 
 // ---- sharded-state plumbing ---------------------------------------------------

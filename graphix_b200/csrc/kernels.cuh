@@ -533,6 +533,85 @@ __global__ void __launch_bounds__(TPB) k_gather(const double2* __restrict__ psi,
   }
 }
 
+// ---------------------------------------------------------------------------
+// k-qubit dense operator (k = 2, 3, 4) on arbitrary axes, in place: each thread owns one group of
+// 2^K amplitudes.  Used by Statevector.evolve (statevec.py:361-395) and by the density-matrix path,
+// where a single-qubit channel is a 2-axis (row bit, column bit) superoperator and a two-qubit
+// channel a 4-axis one.  `offs[b]` = physical offset contributed by operator-index b (precomputed on
+// the host: bit (K-1-i) of b <-> target qubit i).  The matrix sits in shared memory (row-major).
+// Reads S, writes S; 2^K complex FMAs per amplitude (K = 4 is FP64-bound, not HBM-bound).
+// ---------------------------------------------------------------------------
+struct GroupOffsets {
+  unsigned long long off[16];
+};
+template <int K>
+__global__ void __launch_bounds__(TPB) k_evolve(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+                                                const __grid_constant__ GroupOffsets go,
+                                                const double2* __restrict__ op, const uint64_t ngroups) {
+  constexpr int D = 1 << K;
+  __shared__ double2 m[D * D];
+  for (int i = threadIdx.x; i < D * D; i += TPB) m[i] = op[i];
+  __syncthreads();
+  for (uint64_t j = (uint64_t)blockIdx.x * TPB + threadIdx.x; j < ngroups; j += (uint64_t)gridDim.x * TPB) {
+    const uint64_t base = expand(j, hs);
+    double2 v[D];
+#pragma unroll
+    for (int b = 0; b < D; ++b) v[b] = ld_amp(psi + base + go.off[b]);
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int b = 0; b < D; ++b) {
+        const double2 c = m[a * D + b];
+        re = fma(c.x, v[b].x, re);
+        re = fma(-c.y, v[b].y, re);
+        im = fma(c.x, v[b].y, im);
+        im = fma(c.y, v[b].x, im);
+      }
+      st_amp(psi + base + go.off[a], make_double2(re, im));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Density matrices are stored vectorised (|rho>> over row and column qubits).  Traces only touch the
+// 2^n "diagonal" amplitudes rho[x, x]: x is scattered to its row and column bits through byte tables.
+//   acc[0..1] = sum_x sum_ab m[a][b] * rho[(x, t=b), (x, t=a)]   = Tr(op_t rho)      (skipped if !has_target)
+//   acc[2..3] = sum_x sum_a rho[(x, a), (x, a)]                  = Tr(rho)
+// density_matrix.py:263-290 (expectation_single), :354-365 (normalize).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_dm_diag(const double2* __restrict__ psi, const GatherTables* __restrict__ tabs,
+                                                 const uint64_t nx, const int has_target, const uint64_t roff,
+                                                 const uint64_t coff, const double2 m00, const double2 m01,
+                                                 const double2 m10, const double2 m11, double* __restrict__ partials,
+                                                 Ctrl* ctrl, Res* res, const unsigned long long seq) {
+  __shared__ uint64_t st[5][256];
+  for (int i = threadIdx.x; i < 5 * 256; i += TPB) st[i >> 8][i & 255] = tabs->t[i >> 8][i & 255];
+  __syncthreads();
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (uint64_t x = (uint64_t)blockIdx.x * TPB + threadIdx.x; x < nx; x += (uint64_t)gridDim.x * TPB) {
+    const uint64_t base = st[0][x & 255] | st[1][(x >> 8) & 255] | st[2][(x >> 16) & 255] | st[3][(x >> 24) & 255] |
+                          st[4][(x >> 32) & 255];
+    const double2 r00 = __ldg(psi + base);
+    if (has_target) {
+      const double2 r01 = __ldg(psi + base + coff);          // row t = 0, col t = 1
+      const double2 r10 = __ldg(psi + base + roff);          // row t = 1, col t = 0
+      const double2 r11 = __ldg(psi + base + roff + coff);
+      // Tr(op rho) = sum_ab op[a][b] rho[b][a]
+      const double2 t0 = cmad2(m00, r00, m01, r10);
+      const double2 t1 = cmad2(m10, r01, m11, r11);
+      acc[0] += t0.x + t1.x;
+      acc[1] += t0.y + t1.y;
+      acc[2] += r00.x + r11.x;
+      acc[3] += r00.y + r11.y;
+    } else {
+      acc[2] += r00.x;
+      acc[3] += r00.y;
+    }
+  }
+  grid_finish<4>(acc, partials, ctrl, res, seq, FIN_SCALED, 1.0, 1.0);
+}
+
 // g <- 1/sqrt(total * scale), total read from device memory (the all-reduced norm^2 of a sharded projection)
 __global__ void k_set_g(Ctrl* ctrl, const double* __restrict__ total, const double scale) {
   ctrl->g = 1.0 / sqrt(total[0] * scale);

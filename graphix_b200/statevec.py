@@ -240,6 +240,12 @@ class B200Statevector:
         q = (C.c_int * k)(*[int(x) for x in qubits])
         self._check(self._lib.gxsv_evolve(self._h, k, q, a.ctypes.data_as(C.c_void_p)))
 
+    def expectation_value(self, op, qubits: Sequence[int]) -> complex:
+        """<psi| op |psi> for a k-qubit operator — statevec.py:397-415 (same recipe: evolve a copy, then <psi|.>)."""
+        other = B200Statevector(self, device=self._device)
+        other.evolve(op, qubits)
+        return complex(np.dot(self.flatten().conjugate(), other.flatten()))
+
     def remove_qubit(self, qubit: int) -> None:
         """statevec.py:417-428."""
         raise NotImplementedError("This method is deprecated. See :meth:`self.project_qubit`.")

@@ -172,6 +172,19 @@ int gxsv_pack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count,
 int gxsv_unpack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, const void* in_device,
                      double re, double im);
 
+/* ---- density matrices (BASELINE config 5; graphix/sim/density_matrix.py) -------------------------
+ * rho over n qubits is held vectorised as a 2n-qubit register: qubit i has a row qubit rows[i] and a
+ * column qubit cols[i] (logical indices of this handle).  U rho U^dagger = (U on rows[i], conj(U) on
+ * cols[i]) through gxsv_evolve_single / gxsv_evolve; a Kraus channel on k qubits is one 2k-axis
+ * gxsv_evolve with sum_j |c_j|^2 K_j (x) conj(K_j); a rank-1 projection is gxsv_project_qubit on the row
+ * qubit and on the column qubit (GXSV_OPT_DIST = 1 so that no vector norm is imposed), followed by
+ * gxsv_set_norm(Tr^2).  This entry point supplies the traces:
+ *   out[0..1] = Tr(op_target rho)  (density_matrix.py:263-290; skipped when target < 0)
+ *   out[2..3] = Tr(rho)            (density_matrix.py:354-365)
+ * in stored units (their ratio is the normalised expectation value). */
+int gxsv_dm_trace_expect(gxsv_t* h, int npairs, const int* rows, const int* cols, int target, const double m[8],
+                         double out[4]);
+
 /* ---- plumbing -------------------------------------------------------- */
 
 int gxsv_sync(gxsv_t* h);

@@ -160,6 +160,22 @@ class OracleStatevector:
         self._check_bounds(qubit)
         lib().orc_evolve_single(self._psi, _op(op), self._nqubit, int(qubit))
 
+    def evolve(self, op, qubits: Sequence[int]) -> None:  # statevec.py:361-395 (numpy einsum fallback there too)
+        nq = len(qubits)
+        n = self._nqubit
+        op_t = np.asarray(op, dtype=np.complex128).reshape((2,) * (2 * nq))
+        psi_t = self.psi.reshape((2,) * n)
+        out_idx = list(range(n, n + nq))
+        res_idx = list(range(n))
+        for i, q in enumerate(qubits):
+            res_idx[q] = out_idx[i]
+        self._psi[: 1 << n] = np.einsum(op_t, out_idx + list(qubits), psi_t, list(range(n)), res_idx).reshape(1 << n)
+
+    def expectation_value(self, op, qubits: Sequence[int]) -> complex:  # statevec.py:397-415
+        sv = OracleStatevector(self.flatten().copy())
+        sv.evolve(op, qubits)
+        return complex(np.dot(self.flatten().conjugate(), sv.flatten()))
+
     def expectation_single(self, op, qubit: int) -> complex:  # statevec.py:334-359
         self._check_bounds(qubit)
         out = (C.c_double * 2)()

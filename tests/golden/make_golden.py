@@ -153,6 +153,23 @@ def gen_kernels() -> None:
     sv = Statevector(psi, max_qubits=n + 1)
     sv.add_nodes(1, BasicStates.PLUS)
     out["n17_addplus_dig"] = np.array(np.vdot(w, sv.flatten()))
+    # k-qubit operators through Statevector.evolve / expectation_value (statevec.py:361-415); separate rng so that
+    # the arrays above keep their values
+    rng2 = np.random.default_rng(361395)
+    for n in range(2, 7):
+        psi = out[f"n{n}_psi"]
+        for k in (2, 3, 4):
+            if k > n:
+                continue
+            for t in range(3):
+                qs = [int(x) for x in rng2.permutation(n)[:k]]
+                opk = rng2.normal(size=(1 << k, 1 << k)) + 1j * rng2.normal(size=(1 << k, 1 << k))
+                sv = Statevector(psi)
+                out[f"n{n}_ev{k}_{t}_val"] = np.array(sv.expectation_value(opk, qs))
+                sv.evolve(opk, qs)
+                out[f"n{n}_ev{k}_{t}_q"] = np.array(qs)
+                out[f"n{n}_ev{k}_{t}_op"] = opk
+                out[f"n{n}_ev{k}_{t}"] = sv.flatten().copy()
     np.savez_compressed(os.path.join(HERE, "kernels.npz"), **out)
     print("kernels.npz:", len(out), "arrays")
 

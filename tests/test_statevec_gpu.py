@@ -69,6 +69,38 @@ def test_kernels_against_reference_golden(kernels_golden, n):
         np.testing.assert_array_equal(sv.flatten(), g[f"n{n}_perm{t}"])
 
 
+@pytest.mark.parametrize("fusion", [1, 2])
+@pytest.mark.parametrize("n", range(2, 7))
+def test_multi_qubit_evolve_against_reference_golden(kernels_golden, n, fusion):
+    """Statevector.evolve / expectation_value for 2-, 3- and 4-qubit operators on arbitrary qubit tuples."""
+    g = kernels_golden
+    for k in (2, 3, 4):
+        for t in range(3):
+            key = f"n{n}_ev{k}_{t}"
+            if key not in g:
+                continue
+            qs = [int(x) for x in g[key + "_q"]]
+            sv = _sv(g[f"n{n}_psi"], fusion=fusion)
+            assert abs(sv.expectation_value(g[key + "_op"], qs) - complex(g[key + "_val"])) < 1e-12
+            sv.evolve(g[key + "_op"], qs)
+            np.testing.assert_allclose(sv.flatten(), g[key], atol=1e-12)
+    with pytest.raises(ValueError):
+        _sv(g[f"n{n}_psi"]).evolve(np.eye(4), [0, 0])
+
+
+def test_multi_qubit_evolve_large_against_oracle():
+    rng = np.random.default_rng(77)
+    n = 16
+    psi = rand_state(rng, n)
+    dev, orc = _sv(psi), OracleStatevector(psi)
+    for k, qs in ((2, [3, 12]), (3, [15, 0, 7]), (4, [9, 2, 14, 5]), (2, [0, 1])):
+        opk = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+        dev.evolve(opk, qs)
+        orc.evolve(opk, qs)
+        nrm = np.linalg.norm(orc.flatten())
+        np.testing.assert_allclose(dev.flatten() / nrm, orc.flatten() / nrm, atol=1e-12)
+
+
 def test_kernels_17_qubits_golden(kernels_golden):
     g = kernels_golden
     n = 17
