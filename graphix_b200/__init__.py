@@ -7,7 +7,9 @@ behind the C ABI of ``include/gxsv.h``.  There is no CPU fallback.
 """
 from .backend import B200StatevectorBackend, NodeIndex
 from .statevec import B200Statevector
-from . import mbqc
+from .density_matrix import B200DensityMatrix, B200DensityMatrixBackend
+from . import mbqc, noise
 from .simulator import PatternSimulator
 
-__all__ = ["B200StatevectorBackend", "B200Statevector", "NodeIndex", "PatternSimulator", "mbqc"]
+__all__ = ["B200StatevectorBackend", "B200Statevector", "B200DensityMatrix", "B200DensityMatrixBackend", "NodeIndex",
+           "PatternSimulator", "mbqc", "noise"]

@@ -68,6 +68,7 @@ SIGNATURES = {
     "gxsv_set_norm_sink": (C.c_int, [_H, C.c_void_p]),
     "gxsv_set_norm_device": (C.c_int, [_H, C.c_void_p, C.c_double]),
     "gxsv_scale_host": (C.c_int, [_H, C.c_double, C.c_double]),
+    "gxsv_get_hscale": (C.c_int, [_H, _D]),
     "gxsv_scale": (C.c_int, [_H, C.c_double, C.c_double]),
     "gxsv_pack_half": (C.c_int, [_H, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
     "gxsv_unpack_half": (C.c_int, [_H, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_double, C.c_double]),

@@ -1217,6 +1217,12 @@ int gxsv_set_norm_device(gxsv_t* h, const void* device_total, double scale) {
   return check_launch(h, "k_set_g");
 }
 
+int gxsv_get_hscale(gxsv_t* h, double out[2]) {
+  out[0] = h->hscale.real();
+  out[1] = h->hscale.imag();
+  return GXSV_OK;
+}
+
 int gxsv_scale_host(gxsv_t* h, double re, double im) {
   h->hscale *= cplx(re, im);
   return GXSV_OK;

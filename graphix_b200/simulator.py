@@ -69,6 +69,17 @@ class PatternSimulator:
                  measure_method=None, noise_model=None, symbolic: bool = False, stacklevel: int = 1,
                  **backend_kwargs) -> None:
         if isinstance(backend, str):
+            if backend in ("densitymatrix", "b200-densitymatrix"):
+                from .density_matrix import B200DensityMatrixBackend  # noqa: PLC0415
+
+                selector = RandomBranchSelector() if branch_selector is None else branch_selector
+                backend = B200DensityMatrixBackend.with_capacity(pattern.max_space(), branch_selector=selector,
+                                                                 **backend_kwargs)
+                self.backend = backend
+                self.noise_model = noise_model
+                self._pattern = pattern
+                self._measure_method = measure_method or DefaultMeasureMethod()
+                return
             if backend not in ("b200", "statevector"):
                 raise ValueError(f"Unknown backend {backend}.")
             if noise_model is not None:
@@ -115,18 +126,23 @@ class PatternSimulator:
             )
         if input_state is not None:
             backend.add_nodes(pattern.input_nodes, input_state)
-        if self.noise_model is not None:
-            raise ValueError("`noise_model` cannot be specified for state vector backend.")
+        if self.noise_model is None:
+            sequence = pattern
+        else:
+            # simulator.py:437-441: noise on the input nodes, then the noise-transpiled command list
+            sequence = self.noise_model.input_nodes(pattern.input_nodes, rng=rng) if input_state is not None else []
+            sequence.extend(self.noise_model.transpile(pattern, rng=rng))
         pattern.check_runnability()
         mm = self._measure_method
-        for cmd in pattern:
+        noise_model = self.noise_model
+        for cmd in sequence:
             kind = cmd.kind.name
             if kind == "N":
                 backend.add_nodes(nodes=[cmd.node], data=cmd.state)
             elif kind == "E":
                 backend.entangle_nodes(edge=cmd.nodes)
             elif kind == "M":
-                mm.measure(backend, cmd, noise_model=None, rng=rng, stacklevel=stacklevel + 1)
+                mm.measure(backend, cmd, noise_model=noise_model, rng=rng, stacklevel=stacklevel + 1)
             elif kind in ("X", "Z"):
                 if mm.check_domain(cmd.domain):
                     backend.correct_byproduct(cmd)
@@ -134,6 +150,9 @@ class PatternSimulator:
                 backend.apply_clifford(cmd.node, cmd.clifford)
             elif kind == "T":
                 pass
+            elif kind == "ApplyNoise":
+                if cmd.domain is None or mm.check_domain(cmd.domain):
+                    backend.apply_noise(cmd)
             elif kind == "S":
                 raise ValueError("S commands unexpected in simulated patterns.")
             else:

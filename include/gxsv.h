@@ -167,6 +167,7 @@ int gxsv_set_norm(gxsv_t* h, double total_norm2);
 int gxsv_set_norm_sink(gxsv_t* h, void* device_double);
 int gxsv_set_norm_device(gxsv_t* h, const void* device_total, double scale);
 int gxsv_scale_host(gxsv_t* h, double re, double im); /* multiply the pending host scalar (no pass) */
+int gxsv_get_hscale(gxsv_t* h, double out[2]);        /* read the pending host scalar */
 int gxsv_scale(gxsv_t* h, double re, double im);      /* multiply every local amplitude (one pass) */
 int gxsv_pack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, void* out_device);
 int gxsv_unpack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, const void* in_device,

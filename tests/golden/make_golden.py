@@ -378,12 +378,144 @@ def gen_bench_patterns() -> None:
     emit("rand22x3", p, [], meta={"generator": "rand_circuit(22, 3, rng=default_rng(42)) pipeline"})
 
 
+# ---------------------------------------------------------------------------
+# density-matrix path (BASELINE config 5)
+# ---------------------------------------------------------------------------
+def rand_dm(rng, n):
+    a = rng.normal(size=(1 << n, 1 << n)) + 1j * rng.normal(size=(1 << n, 1 << n))
+    rho = a @ a.conj().T
+    return rho / np.trace(rho)
+
+
+def gen_dm_kernels() -> None:
+    from graphix.channels import depolarising_channel, two_qubit_depolarising_channel
+    from graphix.sim.density_matrix import DensityMatrix
+
+    rng = np.random.default_rng(43496)
+    out: dict[str, np.ndarray] = {}
+    for n in range(1, 5):
+        rho = rand_dm(rng, n)
+        out[f"n{n}_rho"] = rho
+        op = rand_op(rng)
+        out[f"n{n}_op"] = op
+        s1 = rand_state(rng, 1)
+        out[f"n{n}_s1"] = s1
+        dm = DensityMatrix(rho)
+        dm.add_nodes(1, BasicStates.PLUS)
+        out[f"n{n}_addplus"] = dm.rho.copy()
+        dm = DensityMatrix(rho)
+        dm.add_nodes(1, s1)
+        out[f"n{n}_add1"] = dm.rho.copy()
+        for q in range(n):
+            dm = DensityMatrix(rho)
+            dm.evolve_single(op, q)
+            out[f"n{n}_evolve_q{q}"] = dm.rho.copy()
+            out[f"n{n}_expect_q{q}"] = np.array(DensityMatrix(rho).expectation_single(op, q))
+            dm = DensityMatrix(rho)
+            dm.apply_channel(depolarising_channel(0.13), [q])
+            out[f"n{n}_depol_q{q}"] = dm.rho.copy()
+            for r in (0, 1):
+                vec = rand_bloch(rng)
+                pm = _outcome_to_operator_matrix(vec, r)
+                out[f"n{n}_proj_q{q}_r{r}_op"] = pm
+                out[f"n{n}_proj_q{q}_r{r}_p"] = np.array(DensityMatrix(rho).expectation_single(pm, q))
+                dm = DensityMatrix(rho)
+                dm.project_qubit(pm, q)
+                out[f"n{n}_proj_q{q}_r{r}"] = dm.rho.copy()
+            for q2 in range(n):
+                if q2 == q:
+                    continue
+                dm = DensityMatrix(rho)
+                dm.entangle((q, q2))
+                out[f"n{n}_cz_{q}_{q2}"] = dm.rho.copy()
+                dm = DensityMatrix(rho)
+                dm.apply_channel(two_qubit_depolarising_channel(0.21), [q, q2])
+                out[f"n{n}_depol2_{q}_{q2}"] = dm.rho.copy()
+                op2 = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+                out[f"n{n}_ev2_{q}_{q2}_op"] = op2
+                dm = DensityMatrix(rho)
+                dm.evolve(op2, [q, q2])
+                out[f"n{n}_ev2_{q}_{q2}"] = dm.rho.copy()
+        perm = [int(x) for x in rng.permutation(n)]
+        dm = DensityMatrix(rho)
+        dm.permute(perm)
+        out[f"n{n}_perm_p"] = np.array(perm)
+        out[f"n{n}_perm"] = dm.rho.copy()
+    np.savez_compressed(os.path.join(HERE, "dm_kernels.npz"), **out)
+    print("dm_kernels.npz:", len(out), "arrays")
+
+
+NOISE = dict(prepare_error_prob=0.01, x_error_prob=0.01, z_error_prob=0.01, entanglement_error_prob=0.01,
+             measure_channel_prob=0.01, measure_error_prob=0.0)
+
+
+def dm_trace(pattern, selector_spec, noise_params, rng_seed, input_state=BasicStates.PLUS, store_rho=True):
+    from graphix.noise_models.depolarising import DepolarisingNoiseModel
+    from graphix.sim.density_matrix import DensityMatrixBackend
+
+    inner = ConstBranchSelector(selector_spec[1]) if selector_spec[0] == "const" else RandomBranchSelector(pr_calc=True)
+    rec = Recording(inner)
+    backend = DensityMatrixBackend(branch_selector=rec)
+    nm = DepolarisingNoiseModel(**noise_params) if noise_params is not None else None
+    sim = PatternSimulator(pattern, backend=backend, noise_model=nm)
+    sim.run(input_state, rng=np.random.default_rng(rng_seed))
+    rho = np.asarray(backend.state.rho)
+    t = {
+        "selector": list(selector_spec), "rng_seed": rng_seed, "input": encode_input(input_state), "noise": noise_params,
+        "p0": {str(k): v for k, v in rec.p0.items()},
+        "outcomes": {str(k): int(v) for k, v in sim.measure_method.results.items()},
+        "trace": float(np.trace(rho).real), "purity": float(np.trace(rho @ rho).real),
+        "diag_head": np.real(np.diag(rho))[:64].tolist(),
+    }
+    if store_rho:
+        t["final_rho"] = np.ascontiguousarray(rho).reshape(-1).view(np.float64).tolist()
+    return t
+
+
+def gen_dm_patterns(big: bool) -> None:
+    os.makedirs(PAT_DIR, exist_ok=True)
+    p = pipeline(rand_circuit(3, 2, rng=np.random.default_rng(42)))
+    emit("dm_rand3x2", p, [dm_trace(p, ("const", 0), NOISE, 7), dm_trace(p, ("const", 1), NOISE, 8),
+                           dm_trace(p, ("random",), NOISE, 9), dm_trace(p, ("random",), None, 10),
+                           dm_trace(p, ("random",), dict(NOISE, measure_error_prob=0.3), 11)])
+    p = Pattern(input_nodes=[0, 1])
+    p.extend([N(2), N(3, PlanarState(Plane.XZ, 0.3)), E((0, 2)), E((1, 2)), E((2, 3)), CmdC(1, Clifford.H),
+              M(0, Measurement.XY(0.31)), M(2, Measurement.YZ(0.27), s_domain={0}), X(3, {2}), Z(3, {0}),
+              CmdC(3, Clifford(13)), Z(1, {2})])
+    inp = [PlanarState(Plane.YZ, 0.6), BasicStates.MINUS]
+    heavy = dict(prepare_error_prob=0.05, x_error_prob=0.1, z_error_prob=0.07, entanglement_error_prob=0.2,
+                 measure_channel_prob=0.15, measure_error_prob=0.0)
+    emit("dm_handbuilt", p, [dm_trace(p, ("const", 0), heavy, 1, inp), dm_trace(p, ("const", 1), heavy, 2, inp),
+                             dm_trace(p, ("random",), heavy, 3, inp)])
+    p = pipeline(rand_circuit(5, 3, rng=np.random.default_rng(42)))
+    emit("dm_rand5x3", p, [dm_trace(p, ("const", 0), NOISE, 7), dm_trace(p, ("random",), NOISE, 5)],
+         meta={"generator": "rand_circuit(5, 3, rng=default_rng(42)) pipeline (config 5 at reduced width)"})
+    if big:
+        import time
+
+        p = pipeline(rand_circuit(9, 3, rng=np.random.default_rng(42)))
+        t0 = time.time()
+        emit("dm_rand9x3", p, [dm_trace(p, ("const", 0), NOISE, 7, store_rho=False)],
+             meta={"generator": "rand_circuit(9, 3, rng=default_rng(42)) pipeline; digests only"})
+        print("  reference DM run took", time.time() - t0, "s")
+        p = pipeline(rand_circuit(12, 3, rng=np.random.default_rng(42)))
+        emit("config5_rand12x3", p, [], meta={"generator": "rand_circuit(12, 3, rng=default_rng(42)) pipeline",
+                                              "noise": NOISE, "selector": "ConstBranchSelector(0)", "rng": "default_rng(7)"})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-bench", action="store_true")
     ap.add_argument("--only-bench", action="store_true")
+    ap.add_argument("--only-dm", action="store_true")
     a = ap.parse_args()
+    if a.only_dm:
+        gen_dm_kernels()
+        gen_dm_patterns(big=True)
+        raise SystemExit(0)
     if not a.only_bench:
+        gen_dm_kernels()
+        gen_dm_patterns(big=False)
         gen_kernels()
         gen_cliffords()
         gen_parity_patterns()

@@ -67,3 +67,36 @@ def check_trace(d: dict, trace: dict, backend_factory) -> None:
 def rand_state(rng, n):
     v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
     return v / np.linalg.norm(v)
+
+
+# ---------------------------------------------------------------------------
+# density-matrix traces
+# ---------------------------------------------------------------------------
+def run_dm_trace(d: dict, trace: dict, backend_factory):
+    from graphix_b200.noise import DepolarisingNoiseModel
+
+    pattern = pattern_from_dict(d)
+    # same selector kind and same seed as the reference run: the rng stream (branch draws + the one
+    # `confuse_result` draw per measurement, depolarising.py:146-147) is then consumed identically
+    inner = mbqc.ConstBranchSelector(trace["selector"][1]) if trace["selector"][0] == "const" else \
+        mbqc.RandomBranchSelector(pr_calc=True)
+    sel = mbqc.RecordingBranchSelector(inner)
+    backend = backend_factory(pattern.max_space(), sel)
+    nm = DepolarisingNoiseModel(**trace["noise"]) if trace["noise"] is not None else None
+    sim = PatternSimulator(pattern, backend=backend, noise_model=nm)
+    sim.run(decode_input(trace["input"]), rng=np.random.default_rng(trace["rng_seed"]))
+    return sel.p0, sim.measure_method.results, backend.state
+
+
+def check_dm_trace(d: dict, trace: dict, backend_factory, atol: float = 1e-10) -> None:
+    p0, outcomes, state = run_dm_trace(d, trace, backend_factory)
+    for k, v in trace["p0"].items():
+        assert abs(p0[int(k)] - v) <= P_TOL, (k, p0[int(k)], v)
+    assert {str(k): int(v) for k, v in outcomes.items()} == trace["outcomes"]
+    rho = np.asarray(state.rho)
+    assert abs(np.trace(rho).real - trace["trace"]) <= 1e-10
+    assert abs(np.trace(rho @ rho).real - trace["purity"]) <= 1e-9
+    np.testing.assert_allclose(np.real(np.diag(rho))[:64], trace["diag_head"], atol=atol)
+    if "final_rho" in trace:
+        ref = np.asarray(trace["final_rho"], dtype=np.float64).view(np.complex128).reshape(rho.shape)
+        np.testing.assert_allclose(rho, ref, atol=atol)
