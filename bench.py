@@ -327,7 +327,7 @@ def gpu_arm(args) -> None:
 
     # ---- end-to-end arm: host input vector in, host final state out ------------
     e2e = None
-    if world == 1:
+    if world == 1 and not args.no_e2e and len(pattern.input_nodes) <= 28:
         n_in = len(pattern.input_nodes)
         n_out = len(pattern.output_nodes)
         host_in = torch.full((1 << n_in,), 2.0 ** (-n_in / 2), dtype=torch.complex128).pin_memory()
@@ -420,6 +420,133 @@ def gpu_arm(args) -> None:
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------
+# density-matrix arm (BASELINE config 5): --workload config5_rand12x3 (or any dm_* fixture)
+# ---------------------------------------------------------------------------
+DM_NOISE = dict(prepare_error_prob=0.01, x_error_prob=0.01, z_error_prob=0.01, entanglement_error_prob=0.01,
+                measure_channel_prob=0.01, measure_error_prob=0.0)
+
+
+def dm_cpu_window(pattern, max_ops: int, budget_s: float = 30.0):
+    """Oracle DM backend (numpy, out of place, one evolve per Kraus operator like the reference) on the first
+    commands of the noisy sequence; stops after ``max_ops`` pattern commands or ``budget_s`` seconds."""
+    from graphix_b200 import mbqc
+    from graphix_b200.noise import DepolarisingNoiseModel
+    from graphix_b200.simulator import DefaultMeasureMethod
+    from oracle.dm_oracle import OracleDMBackend
+
+    nm = DepolarisingNoiseModel(**DM_NOISE)
+    rng = np.random.default_rng(7)
+    backend = OracleDMBackend(branch_selector=mbqc.ConstBranchSelector(0))
+    backend.add_nodes(pattern.input_nodes, mbqc.BasicStates.PLUS)
+    mm = DefaultMeasureMethod()
+    seq = nm.input_nodes(pattern.input_nodes) + nm.transpile(pattern)
+    done = 0
+    t0 = time.perf_counter()
+    for cmd in seq:
+        k = cmd.kind.name
+        if k == "N":
+            backend.add_nodes([cmd.node], cmd.state)
+        elif k == "E":
+            backend.entangle_nodes(cmd.nodes)
+        elif k == "M":
+            mm.measure(backend, cmd, noise_model=nm, rng=rng)
+        elif k in ("X", "Z"):
+            if mm.check_domain(cmd.domain):
+                backend.correct_byproduct(cmd)
+        elif k == "C":
+            backend.apply_clifford(cmd.node, cmd.clifford)
+        elif k == "ApplyNoise":
+            if cmd.domain is None or mm.check_domain(cmd.domain):
+                backend.apply_noise(cmd)
+        if k != "ApplyNoise":
+            done += 1
+        if done >= max_ops or time.perf_counter() - t0 > budget_s:
+            break
+    return done, time.perf_counter() - t0, backend.nqubit
+
+
+def dm_arm(args) -> None:
+    import torch
+
+    from graphix_b200 import B200DensityMatrixBackend, PatternSimulator, _lib, mbqc
+    from graphix_b200.noise import DepolarisingNoiseModel
+    from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern
+
+    name = args.workload
+    pattern = load_pattern(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
+    ncmd = len(pattern)
+    width = pattern.max_space()
+    if args.impl == "reference":
+        done, dt, nq = dm_cpu_window(pattern, args.cpu_window or 10 ** 9, budget_s=60.0)
+        value = done / dt
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1,
+                          "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+                          "config": {"workload": name, "backend": "densitymatrix", "noise": DM_NOISE},
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                           "sample": f"first {done} commands of {name} (+ their noise channels), {dt:.1f} s, "
+                                                     f"numpy density-matrix oracle, reached {nq} qubits"},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+    torch.cuda.set_device(0)
+    backend = B200DensityMatrixBackend.with_capacity(width, branch_selector=mbqc.ConstBranchSelector(0), device=0)
+    nm = DepolarisingNoiseModel(**DM_NOISE)
+
+    def one_step() -> None:
+        backend.state.reset()
+        backend.node_index.clear()
+        PatternSimulator(pattern, backend, noise_model=nm).run(rng=np.random.default_rng(7))
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    backend.state.reset_stats()
+    backend.state.set_option(_lib.OPT_PROFILE, 1)
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    stats = {k: v for k, v in backend.state.stats().items() if v["launches"]}
+    peak, peak_src = measured_peak()
+    dom = max(stats, key=lambda k: stats[k]["device_ms"])
+    d = stats[dom]
+    total_ms = sum(v["device_ms"] for v in stats.values())
+    total_bytes = sum(v["algo_bytes"] for v in stats.values())
+    cpu = None
+    if not args.no_cpu:
+        done, dt, nq = dm_cpu_window(pattern, args.cpu_window or 10 ** 9, budget_s=30.0)
+        cpu = {"value": done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {done} commands of {name} (+ noise channels) in {dt:.1f} s on the numpy density-matrix "
+                         f"oracle, register grown to {nq} of {width} qubits"}
+    line = {
+        "metric": METRIC, "value": ncmd * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": name, "backend": "densitymatrix", "commands_per_step": ncmd, "live_qubits": width,
+                   "rho_bytes_max": 16 << (2 * width), "noise": DM_NOISE, "selector": "ConstBranchSelector(0)",
+                   "rng": "default_rng(7)", "l2": "rho >> 126 MB L2 at full width"},
+        "e2e": None, "gpu_launches": int(sum(v["launches"] for v in stats.values())),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": d["algo_bytes"] / (d["device_ms"] * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": d["algo_bytes"] / (d["device_ms"] * 1e-3) / 1e9 / peak,
+                     "peak_source": peak_src, "traffic": None, "share_of_kernel_time": d["device_ms"] / total_ms,
+                     "all_kernels_frac": total_bytes / (total_ms * 1e-3) / 1e9 / peak,
+                     "kernel_time_share_of_step": total_ms / dev_ms},
+        "cpu_baseline": cpu, "clocks": clocks,
+        "kernels": {k: {"launches_per_step": v["launches"] / args.steps, "ms_per_launch": v["device_ms"] / v["launches"],
+                        "GBps": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9 if v["device_ms"] else None}
+                    for k, v in stats.items()},
+    }
+    print(json.dumps(line))
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -431,6 +558,7 @@ def main() -> None:
                     help="2 = lazy N/E->M fusion (default), 1 = one kernel per command with runs of E fused, 0 = none")
     ap.add_argument("--max-commands", type=int, default=0, help="simulate only the first K commands of the pattern")
     ap.add_argument("--no-per-command", action="store_true", help="skip the secondary fusion=1 measurement")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (it is skipped anyway above 28 input qubits)")
     ap.add_argument("--cprofile", action="store_true", help="host-side cProfile of the timed region (rank 0, stderr)")
     ap.add_argument("--strict", dest="nonstrict", action="store_false",
                     help="N > 1: wait for the all-reduced norm of every projection (default: deferred check at finalize)")
@@ -438,7 +566,9 @@ def main() -> None:
     ap.add_argument("--cpu-window", type=int, default=0, help="commands per CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload and args.workload.startswith(("config5", "dm_")):
+        dm_arm(args)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         gpu_arm(args)

@@ -178,7 +178,7 @@ def _need(world: int) -> None:
         pytest.skip(f"needs {world} GPUs")
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_gpu_golden(world):
     _need(world)
     out = run_case("golden", world)
