@@ -92,28 +92,30 @@ class B200StatevectorBackend(_Base):  # type: ignore[misc, valid-type]
     """
 
     def __init__(self, state: B200Statevector | None = None, *, node_index=None, branch_selector=None,
-                 symbolic: bool = False, device: int | None = None, fusion: int = 1, strict: bool = True) -> None:
+                 symbolic: bool = False, device: int | None = None, fusion: int = 2, strict: bool = True) -> None:
         if symbolic:
             raise ValueError(
                 "Statevector backend does not support `symbolic` simulation. Consider using backend in `graphix-symbolic` plugin."
             )
         if state is None:
             state = B200Statevector(nqubit=0, device=device, fusion=fusion, strict=strict)
-        elif not isinstance(state, B200Statevector):
+        elif not isinstance(state, B200Statevector) and not hasattr(state, "project_qubit"):
             state = B200Statevector(state, device=device, fusion=fusion, strict=strict)
+        # (any other object with the DenseState surface — project_qubit, expectation_single, ... — is used as is
+        #  through the generic calls below; this is how the host logic is exercised without a GPU in the tests)
         set_ = object.__setattr__  # the graphix base is a frozen dataclass
         set_(self, "state", state)
         set_(self, "node_index", NodeIndex() if node_index is None else node_index)
         set_(self, "branch_selector", RandomBranchSelector() if branch_selector is None else branch_selector)
         set_(self, "symbolic", False)
-        set_(self, "_lib", state._lib)
+        set_(self, "_lib", getattr(state, "_lib", None))
         set_(self, "_op", (C.c_double * 8)())
 
     @classmethod
     def with_capacity(cls, max_qubits: int, state=None, **kwargs) -> "B200StatevectorBackend":
         """Preallocate ``2**max_qubits`` amplitudes — statevec.py:807-832."""
         dev = kwargs.pop("device", None)
-        fusion = kwargs.pop("fusion", 1)
+        fusion = kwargs.pop("fusion", 2)
         strict = kwargs.pop("strict", True)
         if state is None:
             st = B200Statevector(nqubit=0, max_qubits=max_qubits, device=dev, fusion=fusion, strict=strict)
@@ -161,8 +163,18 @@ class B200StatevectorBackend(_Base):  # type: ignore[misc, valid-type]
             op[6] = 0.5 - 0.5 * sign * z
             op[7] = 0.0
 
+        def as_matrix():
+            import numpy as np  # noqa: PLC0415
+
+            return np.array([[complex(op[0], op[1]), complex(op[2], op[3])],
+                             [complex(op[4], op[5]), complex(op[6], op[7])]])
+
         def f_expectation0() -> float:
             fill(1.0)
+            if self._lib is None:
+                v = state.expectation_single(as_matrix(), loc)
+                assert abs(v.imag) <= 1e-10
+                return v.real
             out = (C.c_double * 2)()
             state._check(self._lib.gxsv_expectation_single(state._h, loc, op, out))
             assert abs(out[1]) <= 1e-10
@@ -170,7 +182,10 @@ class B200StatevectorBackend(_Base):  # type: ignore[misc, valid-type]
 
         outcome = self.branch_selector.measure(node, f_expectation0, rng, stacklevel=stacklevel + 1)
         fill(-1.0 if outcome else 1.0)
-        state._check(self._lib.gxsv_project_qubit(state._h, loc, op, 1e-10, None))
+        if self._lib is None:
+            state.project_qubit(as_matrix(), loc)
+        else:
+            state._check(self._lib.gxsv_project_qubit(state._h, loc, op, 1e-10, None))
         self.node_index.remove(node)
         return outcome
 

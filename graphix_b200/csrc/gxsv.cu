@@ -63,6 +63,7 @@ struct gxsv {
   Res* ring_dev = nullptr;
   unsigned long long seq = 0;
   GatherTables* tabs_dev = nullptr;
+  double2* op_dev = nullptr;   // 16x16 operator scratch for gxsv_evolve
   double2* stage[2] = {nullptr, nullptr};
   size_t stage_amps = 0;
   // options
@@ -498,6 +499,7 @@ int init_common(gxsv_t* h) {
   CU(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
   CU(cudaMalloc(&h->partials, sizeof(double) * 4 * (size_t)(h->sm_count * 8 + 8)));
   CU(cudaMalloc(&h->tabs_dev, sizeof(GatherTables)));
+  CU(cudaMalloc(&h->op_dev, sizeof(double2) * 256));
   CU(cudaHostAlloc(&h->ring_host, sizeof(Res) * RING, cudaHostAllocMapped));
   memset(h->ring_host, 0, sizeof(Res) * RING);
   CU(cudaHostGetDevicePointer((void**)&h->ring_dev, h->ring_host, 0));
@@ -570,6 +572,7 @@ int gxsv_destroy(gxsv_t* h) {
   if (h->ctrl) cudaFree(h->ctrl);
   if (h->partials) cudaFree(h->partials);
   if (h->tabs_dev) cudaFree(h->tabs_dev);
+  if (h->op_dev) cudaFree(h->op_dev);
   if (h->ring_host) cudaFreeHost(h->ring_host);
   for (int i = 0; i < 2; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
   delete h;
@@ -821,8 +824,9 @@ int gxsv_evolve(gxsv_t* h, int k, const int* qubits, const double* op) {
     for (int i = 0; i < k; ++i) skip = skip || (h->q[qubits[i]].phys == b);
     if (skip) hs.pos[hs.n++] = (unsigned char)b;
   }
-  double2* dop = nullptr;
-  CU(cudaMalloc(&dop, sizeof(double2) * D * D));
+  // the scratch is rewritten by the next evolve: stream order keeps this launch's copy intact, and the
+  // (pageable) host source is consumed before cudaMemcpyAsync returns
+  double2* dop = h->op_dev;
   CU(cudaMemcpyAsync(dop, op, sizeof(double2) * D * D, cudaMemcpyHostToDevice, h->stream));
   const uint64_t ngroups = 1ull << (n - k);
   const int grid = grid_for(h, ngroups, 1);
@@ -832,10 +836,7 @@ int gxsv_evolve(gxsv_t* h, int k, const int* qubits, const double* op) {
     else if (k == 3) k_evolve<3><<<grid, TPB, 0, h->stream>>>(h->psi, hs, go, dop, ngroups);
     else k_evolve<4><<<grid, TPB, 0, h->stream>>>(h->psi, hs, go, dop, ngroups);
   }
-  int rc = check_launch(h, "k_evolve");
-  CU(cudaStreamSynchronize(h->stream));
-  CU(cudaFree(dop));
-  return rc;
+  return check_launch(h, "k_evolve");
 }
 
 int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) {

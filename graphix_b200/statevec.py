@@ -64,12 +64,12 @@ class B200Statevector:
     ``State``, an iterable of ``State``, a ``2**n`` vector or another statevector;
     ``max_qubits`` preallocates capacity (``Pattern.max_space()``).
     Extra keyword-only parameters: ``device`` (CUDA ordinal), ``fusion``
-    (0 = one kernel per command, 1 = runs of E fused [default], 2 = lazy N/E->M),
+    (0 = one kernel per command, 1 = runs of E fused, 2 = lazy N/E->M fusion [default]),
     ``strict`` (wait for every projection norm, default True).
     """
 
     def __init__(self, data=BasicStates.PLUS, nqubit: int | None = None, max_qubits: int | None = None, *,
-                 device: int | None = None, fusion: int = 1, strict: bool = True) -> None:
+                 device: int | None = None, fusion: int = 2, strict: bool = True) -> None:
         if nqubit is not None and nqubit < 0:
             raise ValueError("`nqubit` must be a non-negative integer.")
         if max_qubits is not None and max_qubits < 0:

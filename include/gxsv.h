@@ -49,7 +49,8 @@ enum {
 
 /* option keys for gxsv_set_option */
 enum {
-  GXSV_OPT_FUSION = 1,  /* 0 = one kernel per command, 1 = fuse runs of E (default), 2 = lazy N/E->M fusion */
+  GXSV_OPT_FUSION = 1,  /* 0 = one kernel per command, 1 = fuse runs of E (library default), 2 = lazy N/E->M fusion
+                         * (default of the Python backend) */
   GXSV_OPT_STRICT = 2,  /* 1 (default) = project_qubit waits for the norm and raises like the reference */
   GXSV_OPT_PROFILE = 3, /* 1 = bracket every launch with CUDA events (read back through gxsv_stats) */
   GXSV_OPT_DIST = 4     /* 1 = this handle is one shard of a distributed state (see the sharded section) */
