@@ -19,7 +19,9 @@ def golden_pattern_names(with_traces: bool = True) -> list[str]:
     names = []
     for p in sorted(glob.glob(os.path.join(GOLDEN, "patterns", "*.json.gz"))):
         name = os.path.basename(p)[: -len(".json.gz")]
-        if with_traces and name.startswith(("config2", "config3", "config4", "rand20", "rand22")):
+        if name.startswith(("dm_", "config5")):
+            continue                                     # density-matrix fixtures: tests/test_dm_*.py
+        if with_traces and name.startswith(("config2", "config3", "config4", "rand20", "rand22", "scale_")):
             continue
         names.append(name)
     return names
