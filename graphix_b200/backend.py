@@ -92,15 +92,16 @@ class B200StatevectorBackend(_Base):  # type: ignore[misc, valid-type]
     """
 
     def __init__(self, state: B200Statevector | None = None, *, node_index=None, branch_selector=None,
-                 symbolic: bool = False, device: int | None = None, fusion: int = 2, strict: bool = True) -> None:
+                 symbolic: bool = False, device: int | None = None, fusion: int = 2, strict: bool = True,
+                 batch: int = 0) -> None:
         if symbolic:
             raise ValueError(
                 "Statevector backend does not support `symbolic` simulation. Consider using backend in `graphix-symbolic` plugin."
             )
         if state is None:
-            state = B200Statevector(nqubit=0, device=device, fusion=fusion, strict=strict)
+            state = B200Statevector(nqubit=0, device=device, fusion=fusion, strict=strict, batch=batch)
         elif not isinstance(state, B200Statevector) and not hasattr(state, "project_qubit"):
-            state = B200Statevector(state, device=device, fusion=fusion, strict=strict)
+            state = B200Statevector(state, device=device, fusion=fusion, strict=strict, batch=batch)
         # (any other object with the DenseState surface — project_qubit, expectation_single, ... — is used as is
         #  through the generic calls below; this is how the host logic is exercised without a GPU in the tests)
         set_ = object.__setattr__  # the graphix base is a frozen dataclass
@@ -117,10 +118,11 @@ class B200StatevectorBackend(_Base):  # type: ignore[misc, valid-type]
         dev = kwargs.pop("device", None)
         fusion = kwargs.pop("fusion", 2)
         strict = kwargs.pop("strict", True)
+        batch = kwargs.pop("batch", 0)
         if state is None:
-            st = B200Statevector(nqubit=0, max_qubits=max_qubits, device=dev, fusion=fusion, strict=strict)
+            st = B200Statevector(nqubit=0, max_qubits=max_qubits, device=dev, fusion=fusion, strict=strict, batch=batch)
         else:
-            st = B200Statevector(state, max_qubits=max_qubits, device=dev, fusion=fusion, strict=strict)
+            st = B200Statevector(state, max_qubits=max_qubits, device=dev, fusion=fusion, strict=strict, batch=batch)
         return cls(st, **kwargs)
 
     # -- Backend contract -------------------------------------------------------
@@ -211,6 +213,9 @@ class B200StatevectorBackend(_Base):  # type: ignore[misc, valid-type]
         self.state.permute([self.node_index.index(node) for node in output_nodes])
         self.node_index.clear()
         self.node_index.extend(output_nodes)
+        sync = getattr(self.state, "sync", None)
+        if sync is not None:
+            sync()    # non-strict mode: deferred zero-norm errors of the run surface here at the latest
 
     def __repr__(self) -> str:
         return f"B200StatevectorBackend(state={self.state!r}, branch_selector={self.branch_selector!r})"

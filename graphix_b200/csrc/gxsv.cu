@@ -70,6 +70,9 @@ struct gxsv {
   int fusion = 1;
   int strict = 1;
   int profile = 0;
+  int batch_max = 0;       // > 0: queue up to this many fused projections and run them in one pass (non-strict only)
+  Batch batch;             // the open batch (nstages == 0: none)
+  std::vector<std::pair<unsigned long long, int>> deferred;  // (result slot, stages) awaiting their norm check
   double* sink = nullptr;  // device slot for local norms (sharded, see gxsv_set_norm_sink)
   int dist = 0;            // sharded: projections publish local norms, the host sets g after the all-reduce
   int sm_count = 148;
@@ -149,11 +152,14 @@ cudaEvent_t get_event(gxsv_t* h) {
   return e;
 }
 
+int flush_batch(gxsv_t* h);
+
 struct Launch {
   gxsv_t* h;
   int kind;
   cudaEvent_t e0 = nullptr;
   Launch(gxsv_t* h_, int kind_, double bytes) : h(h_), kind(kind_) {
+    if (h->batch.nstages) flush_batch(h);   // queued projections go first: everything else sees their result
     h->stats.launches[kind] += 1;
     h->stats.algo_bytes[kind] += bytes;
     if (h->profile) {
@@ -189,7 +195,7 @@ Res* next_slot(gxsv_t* h, unsigned long long* seq_out) {
   return h->ring_dev + (h->seq % RING);
 }
 
-int wait_slot(gxsv_t* h, unsigned long long seq, double out[4]) {
+int wait_slot(gxsv_t* h, unsigned long long seq, double out[8]) {
   volatile Res* r = h->ring_host + (seq % RING);
   unsigned long spins = 0;
   while (r->seq != seq) {
@@ -205,13 +211,61 @@ int wait_slot(gxsv_t* h, unsigned long long seq, double out[4]) {
     }
   }
   __sync_synchronize();
-  for (int i = 0; i < 4; ++i) out[i] = r->v[i];
+  for (int i = 0; i < 8; ++i) out[i] = r->v[i];
   return GXSV_OK;
 }
 
 int check_launch(gxsv_t* h, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, GXSV_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return GXSV_OK;
+}
+
+// Run the queued projection stages (k_fused_batch).  The layout bookkeeping was done when they were queued.
+int flush_batch(gxsv_t* h) {
+  if (h->batch.nstages == 0) return GXSV_OK;
+  Batch bt = h->batch;
+  h->batch.nstages = 0;
+  h->batch.naxes = 0;
+  Holes hs;
+  hs.n = 0;
+  for (int b = 0; b < h->phys_bits; ++b) {
+    bool skip = !((h->live_mask >> b) & 1ull);
+    for (int a = 0; a < bt.naxes; ++a) skip = skip || (bt.axbit[a] == b);
+    if (skip) hs.pos[hs.n++] = (unsigned char)b;
+  }
+  const int n = __builtin_popcountll(h->live_mask);
+  const uint64_t ngroups = 1ull << (n - bt.naxes);
+  unsigned long long seq;
+  Res* slot = next_slot(h, &seq);
+  const int grid = grid_for(h, ngroups, 1);
+  {
+    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
+    if (bt.naxes == 1) k_fused_batch<1><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq);
+    else if (bt.naxes == 2) k_fused_batch<2><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq);
+    else k_fused_batch<3><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq);
+  }
+  h->deferred.push_back({seq, bt.nstages});
+  return check_launch(h, "k_fused_batch");
+}
+
+// Non-strict mode: verify the norms of the projections issued so far (statevec.py:1192-1193, raised late).
+int check_deferred(gxsv_t* h) {
+  int rc = flush_batch(h);
+  if (rc) return rc;
+  if (h->deferred.empty()) return GXSV_OK;
+  std::vector<std::pair<unsigned long long, int>> todo;
+  todo.swap(h->deferred);
+  for (auto& d : todo) {
+    double v[8];
+    rc = wait_slot(h, d.first, v);
+    if (rc) return rc;
+    double prev = 1.0;
+    for (int k = 0; k < d.second; ++k) {
+      if (!(v[k] > 1e-10 * prev)) return fail(h, GXSV_EZERONORM, "Attempted to remove a qubit from 0-norm statevector (detected at sync).");
+      prev = v[k];
+    }
+  }
   return GXSV_OK;
 }
 
@@ -497,13 +551,14 @@ int init_common(gxsv_t* h) {
   CU(cudaGetDeviceProperties(&prop, h->device));
   h->sm_count = prop.multiProcessorCount;
   CU(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
-  CU(cudaMalloc(&h->partials, sizeof(double) * 4 * (size_t)(h->sm_count * 8 + 8)));
+  CU(cudaMalloc(&h->partials, sizeof(double) * 8 * (size_t)(h->sm_count * 8 + 8)));
   CU(cudaMalloc(&h->tabs_dev, sizeof(GatherTables)));
   CU(cudaMalloc(&h->op_dev, sizeof(double2) * 256));
   CU(cudaHostAlloc(&h->ring_host, sizeof(Res) * RING, cudaHostAllocMapped));
   memset(h->ring_host, 0, sizeof(Res) * RING);
   CU(cudaHostGetDevicePointer((void**)&h->ring_dev, h->ring_host, 0));
   memset(&h->stats, 0, sizeof h->stats);
+  memset(&h->batch, 0, sizeof h->batch);
   return gxsv_reset(h);
 }
 
@@ -581,6 +636,14 @@ int gxsv_destroy(gxsv_t* h) {
 
 int gxsv_reset(gxsv_t* h) {
   CU(cudaSetDevice(h->device));
+  {
+    // projections still in flight are verified before the register is thrown away
+    int rc = (h->ctrl && h->ring_host) ? check_deferred(h) : GXSV_OK;
+    h->batch.nstages = 0;
+    h->batch.naxes = 0;
+    h->deferred.clear();
+    if (rc) return rc;
+  }
   h->q.clear();
   h->pend.clear();
   h->next_id = 0;
@@ -603,12 +666,20 @@ int gxsv_set_option(gxsv_t* h, int key, int value) {
       { int rc = gxsv_flush(h); if (rc) return rc; }
       h->fusion = value;
       return GXSV_OK;
-    case GXSV_OPT_STRICT: h->strict = value ? 1 : 0; return GXSV_OK;
+    case GXSV_OPT_STRICT:
+      if (value) { int rc = check_deferred(h); if (rc) return rc; }
+      h->strict = value ? 1 : 0;
+      return GXSV_OK;
     case GXSV_OPT_PROFILE:
       if (!value) prof_collect(h);
       h->profile = value ? 1 : 0;
       return GXSV_OK;
     case GXSV_OPT_DIST: h->dist = value ? 1 : 0; return GXSV_OK;
+    case GXSV_OPT_BATCH:
+      if (value < 0 || value > MAX_STAGES) return fail(h, GXSV_EVALUE, "batch must be in [0, %d]", (int)MAX_STAGES);
+      { int rc = flush_batch(h); if (rc) return rc; }
+      h->batch_max = value;
+      return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -619,6 +690,7 @@ int gxsv_get_option(gxsv_t* h, int key, int* value) {
     case GXSV_OPT_STRICT: *value = h->strict; return GXSV_OK;
     case GXSV_OPT_PROFILE: *value = h->profile; return GXSV_OK;
     case GXSV_OPT_DIST: *value = h->dist; return GXSV_OK;
+    case GXSV_OPT_BATCH: *value = h->batch_max; return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -631,6 +703,7 @@ int gxsv_ensure_capacity(gxsv_t* h, int required_qubits) {
   if (required_qubits > 40) return fail(h, GXSV_EVALUE, "capacity of %d qubits exceeds the 40-qubit index space", required_qubits);
   if (!h->own_buf) return fail(h, GXSV_ENOMEM, "external buffer of 2^%d amplitudes cannot grow to 2^%d", h->cap_bits, required_qubits);
   CU(cudaSetDevice(h->device));
+  { int rc = flush_batch(h); if (rc) return rc; }
   double2* nb = nullptr;
   CU(cudaMalloc(&nb, sizeof(double2) << required_qubits));
   CU(cudaMemcpyAsync(nb, h->psi, sizeof(double2) << h->phys_bits, cudaMemcpyDeviceToDevice, h->stream));
@@ -658,7 +731,9 @@ int gxsv_tensor(gxsv_t* h, int k, const double* vec) {
   CU(cudaSetDevice(h->device));
   if (k < 0 || k > 30) return fail(h, GXSV_EVALUE, "tensor: k = %d out of range", k);
   if (k == 0) { h->hscale *= cplx(vec[0], vec[1]); return GXSV_OK; }
-  int rc = flush_pending(h);
+  int rc = flush_batch(h);
+  if (rc) return rc;
+  rc = flush_pending(h);
   if (rc) return rc;
   const int n = nlive_bits(h);
   const uint64_t nnew = 1ull << k;
@@ -859,7 +934,7 @@ int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) 
   }
   rc = check_launch(h, "k_pair_reduce");
   if (rc) return rc;
-  double v[4];
+  double v[8];
   rc = wait_slot(h, seq, v);
   if (rc) return rc;
   out[0] = v[0];
@@ -876,7 +951,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
   if (r0 + r1 == 0.0) return fail(h, GXSV_EZERONORM, "Attempted to remove qubit %d from 0-norm statevector.", q);
   const double det = std::abs(m00 * m11 - m01 * m10);
   const bool rank1 = det <= 1e-13 * (r0 + r1);
-  double v[4];
+  double v[8];
   unsigned long long seq;
   if (rank1) {
     // op = u w^T: row r = u_r * w.  Contract with the larger row (best conditioned); the two half-norms the
@@ -934,6 +1009,33 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
       } else {
         const int p = h->q[q].phys;
         const cplx s0 = h->q[vi].s0, s1 = h->q[vi].s1;
+        if (h->batch_max > 0 && !h->strict && !h->dist) {
+          // non-strict: queue the butterfly; up to batch_max stages on <= 3 distinct bits run as one pass
+          int ax = -1;
+          for (int a = 0; a < h->batch.naxes; ++a) if (h->batch.axbit[a] == p) ax = a;
+          if (h->batch.nstages >= std::min(h->batch_max, (int)MAX_STAGES) || (ax < 0 && h->batch.naxes >= 3)) {
+            rc = flush_batch(h);
+            if (rc) return rc;
+            ax = -1;
+          }
+          if (ax < 0) { ax = h->batch.naxes++; h->batch.axbit[ax] = (unsigned char)p; }
+          Stage& st = h->batch.st[h->batch.nstages++];
+          st.m00 = d2(s0 * c0); st.m01 = d2(s0 * c1); st.m10 = d2(s1 * c0); st.m11 = d2(-s1 * c1);
+          st.mq = mq; st.mv = mv; st.axis = ax; st.pad = 0;
+          h->q[vi].phys = p;
+          h->q.erase(h->q.begin() + q);
+          h->hscale = 1.0;
+          if (big == 1 && r0 > 1e-10 * r1) {
+            // the reference keeps half 0 whenever its norm is above the cut-off: same phase convention
+            const cplx ub = std::abs(m10) >= std::abs(m11) ? m10 : m11;
+            const cplx up = std::abs(m10) >= std::abs(m11) ? m00 : m01;
+            const cplx ratio = up / ub;
+            if (std::abs(ratio) > 0.0) h->hscale *= ratio / std::abs(ratio);
+          }
+          if (h->deferred.size() > (size_t)(RING - 16)) { rc = check_deferred(h); if (rc) return rc; }
+          if (norms) { norms[0] = norms[1] = NAN; }
+          return GXSV_OK;
+        }
         const int n = nlive_bits(h);
         const uint64_t npair = 1ull << (n - 1);
         Holes hs = make_holes(h, p);
@@ -952,6 +1054,14 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     }
     h->hscale = 1.0;
     if (!h->strict && !h->dist) {
+      h->deferred.push_back({seq, 1});
+      if (big == 1 && r0 > 1e-10 * r1) {
+        const cplx ub = std::abs(m10) >= std::abs(m11) ? m10 : m11;
+        const cplx up = std::abs(m10) >= std::abs(m11) ? m00 : m01;
+        const cplx ratio = up / ub;
+        if (std::abs(ratio) > 0.0) h->hscale *= ratio / std::abs(ratio);
+      }
+      if (h->deferred.size() > (size_t)(RING - 16)) { rc = check_deferred(h); if (rc) return rc; }
       if (norms) { norms[0] = norms[1] = NAN; }
       return GXSV_OK;
     }
@@ -1048,7 +1158,9 @@ int gxsv_flatten_device(gxsv_t* h, void* out_device) {
 
 int gxsv_flatten(gxsv_t* h, double* out_host) {
   CU(cudaSetDevice(h->device));
-  int rc = flush_pending(h);
+  int rc = check_deferred(h);
+  if (rc) return rc;
+  rc = flush_pending(h);
   if (rc) return rc;
   rc = upload_tables(h);
   if (rc) return rc;
@@ -1083,7 +1195,7 @@ int gxsv_norm2(gxsv_t* h, double* out) {
   }
   rc = check_launch(h, "k_norm2");
   if (rc) return rc;
-  double v[4];
+  double v[8];
   rc = wait_slot(h, seq, v);
   if (rc) return rc;
   *out = v[0];
@@ -1111,7 +1223,7 @@ int gxsv_fidelity(gxsv_t* a, gxsv_t* b, double* out) {
       k_inner<U_DEF><<<grid_for(a, total, U_DEF), TPB, 0, a->stream>>>(xa, xb, total, a->partials, a->ctrl, slot, seq);
     }
     rc = check_launch(a, "k_inner");
-    double v[4];
+    double v[8];
     if (!rc) rc = wait_slot(a, seq, v);
     if (!rc) *out = v[0] * v[0] + v[1] * v[1];
   }
@@ -1171,7 +1283,7 @@ int gxsv_dm_trace_expect(gxsv_t* h, int npairs, const int* rows, const int* cols
   }
   rc = check_launch(h, "k_dm_diag");
   if (rc) return rc;
-  double v[4];
+  double v[8];
   rc = wait_slot(h, seq, v);
   if (rc) return rc;
   for (int i = 0; i < 4; ++i) out[i] = v[i];
@@ -1274,11 +1386,13 @@ int gxsv_unpack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t coun
 
 int gxsv_sync(gxsv_t* h) {
   CU(cudaSetDevice(h->device));
+  int rc = check_deferred(h);   // runs queued projections and raises their zero-norm errors (non-strict mode)
   CU(cudaStreamSynchronize(h->stream));
-  return GXSV_OK;
+  return rc;
 }
 
 int gxsv_stats(gxsv_t* h, gxsv_stats_t* out) {
+  flush_batch(h);
   prof_collect(h);
   *out = h->stats;
   return GXSV_OK;

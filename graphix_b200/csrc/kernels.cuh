@@ -36,9 +36,9 @@ struct Ctrl {            // device-resident control block
 };
 
 struct Res {             // one slot of the host-mapped result ring
-  double v[4];
+  double v[8];
   unsigned long long seq;
-  unsigned long long pad[3];
+  unsigned long long pad[7];
 };
 
 __device__ __forceinline__ uint64_t expand(uint64_t x, const Holes& h) {
@@ -98,7 +98,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* NV*8 
   }
 }
 
-enum { FIN_CONTRACT = 0, FIN_SCALED = 1, FIN_CONTRACT_DIST = 2 };
+enum { FIN_CONTRACT = 0, FIN_SCALED = 1, FIN_CONTRACT_DIST = 2, FIN_BATCH = 3 };
 
 // Writes the block partial, elects the last block, which sums all partials in a
 // fixed order and publishes the result to the host-mapped slot.
@@ -107,6 +107,7 @@ enum { FIN_CONTRACT = 0, FIN_SCALED = 1, FIN_CONTRACT_DIST = 2 };
 //   FIN_SCALED  : v[k] *= post * g^2 (expectation values / norms of the true state).
 //   FIN_CONTRACT_DIST: sharded state — publish the local sum only; g is set by the host after the
 //                 all-reduce over ranks (gxsv_set_norm).
+//   FIN_BATCH    : a batch of `post` projection stages: v[k] = norm^2 after stage k; g = 1/sqrt(v[post-1]).
 template <int NV>
 __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restrict__ partials, Ctrl* ctrl,
                                             Res* res, unsigned long long seq, int mode, double post, double g) {
@@ -139,6 +140,10 @@ __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restric
     } else if (mode == FIN_CONTRACT_DIST) {
       res->v[0] = tot[0];
       if (ctrl->sink) ctrl->sink[0] = tot[0];
+    } else if (mode == FIN_BATCH) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) res->v[k] = tot[k];
+      ctrl->g = 1.0 / sqrt(tot[(int)post - 1]);
     } else {
 #pragma unroll
       for (int k = 0; k < NV; ++k) res->v[k] = tot[k] * post * g * g;
@@ -349,6 +354,84 @@ __global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const 
     }
   }
   grid_finish<1>(acc, partials, ctrl, res, seq, fin_mode, 1.0, g);
+}
+
+// ---------------------------------------------------------------------------
+// Batched lazy projections (non-strict mode).  Up to MAX_STAGES consecutive fused N,E..,M butterflies are
+// queued on the host and executed in ONE pass: the stages act on at most A distinct physical bits, a thread
+// owns the 2^A amplitudes of one group in registers and applies the stages in order (each stage is the
+// k_fused butterfly on its own axis, sign masks evaluated on the current index bits), accumulating the
+// norm^2 after every stage.  K stages cost 2 S instead of 2 K S.
+// ---------------------------------------------------------------------------
+constexpr int MAX_STAGES = 8;
+struct Stage {
+  double2 m00, m01, m10, m11;
+  unsigned long long mq, mv;
+  int axis;
+  int pad;
+};
+struct Batch {
+  int nstages;
+  int naxes;
+  unsigned char axbit[8];
+  Stage st[MAX_STAGES];
+};
+template <int A>
+__global__ void __launch_bounds__(TPB) k_fused_batch(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+                                                     const __grid_constant__ Batch bt, const uint64_t ngroups,
+                                                     double* __restrict__ partials, Ctrl* ctrl, Res* res,
+                                                     const unsigned long long seq) {
+  constexpr int D = 1 << A;
+  const double g = ctrl->g;
+  uint64_t off[D];
+#pragma unroll
+  for (int b = 0; b < D; ++b) {
+    uint64_t o = 0;
+#pragma unroll
+    for (int a = 0; a < A; ++a)
+      if ((b >> a) & 1) o |= 1ull << bt.axbit[a];
+    off[b] = o;
+  }
+  double acc[MAX_STAGES];
+#pragma unroll
+  for (int k = 0; k < MAX_STAGES; ++k) acc[k] = 0.0;
+  for (uint64_t j = (uint64_t)blockIdx.x * TPB + threadIdx.x; j < ngroups; j += (uint64_t)gridDim.x * TPB) {
+    const uint64_t base = expand(j, hs);
+    double2 v[D];
+#pragma unroll
+    for (int b = 0; b < D; ++b) v[b] = ld_amp(psi + base + off[b]);
+#pragma unroll
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      if (s < bt.nstages) {
+        const Stage& st = bt.st[s];
+        const double sc = (s == 0) ? g : 1.0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          if (st.axis == a) {
+#pragma unroll
+            for (int lo = 0; lo < D; ++lo) {
+              if ((lo >> a) & 1) continue;
+              const int hi = lo | (1 << a);
+              const uint64_t idx = base + off[lo];
+              const double sq = ((__popcll(idx & st.mq) & 1) ? -sc : sc);
+              const double sv = (__popcll(idx & st.mv) & 1) ? -1.0 : 1.0;
+              const double2 t0 = make_double2(sc * v[lo].x, sc * v[lo].y);
+              const double2 t1 = make_double2(sq * v[hi].x, sq * v[hi].y);
+              const double2 r0 = cmad2(st.m00, t0, st.m01, t1);
+              double2 r1 = cmad2(st.m10, t0, st.m11, t1);
+              r1.x *= sv; r1.y *= sv;
+              acc[s] += cnorm2(r0) + cnorm2(r1);
+              v[lo] = r0;
+              v[hi] = r1;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < D; ++b) st_amp(psi + base + off[b], v[b]);
+  }
+  grid_finish<MAX_STAGES>(acc, partials, ctrl, res, seq, FIN_BATCH, (double)bt.nstages, g);
 }
 
 // ---------------------------------------------------------------------------

@@ -65,11 +65,13 @@ class B200Statevector:
     ``max_qubits`` preallocates capacity (``Pattern.max_space()``).
     Extra keyword-only parameters: ``device`` (CUDA ordinal), ``fusion``
     (0 = one kernel per command, 1 = runs of E fused, 2 = lazy N/E->M fusion [default]),
-    ``strict`` (wait for every projection norm, default True).
+    ``strict`` (wait for every projection norm, default True; with ``strict=False`` the zero-norm
+    ``RuntimeError`` surfaces at ``sync()`` / ``flatten()`` / ``finalize``), ``batch`` (K > 0 with
+    ``strict=False``: up to K consecutive fused projections run as ONE pass over the register).
     """
 
     def __init__(self, data=BasicStates.PLUS, nqubit: int | None = None, max_qubits: int | None = None, *,
-                 device: int | None = None, fusion: int = 2, strict: bool = True) -> None:
+                 device: int | None = None, fusion: int = 2, strict: bool = True, batch: int = 0) -> None:
         if nqubit is not None and nqubit < 0:
             raise ValueError("`nqubit` must be a non-negative integer.")
         if max_qubits is not None and max_qubits < 0:
@@ -88,6 +90,10 @@ class B200Statevector:
             _lib.raise_for(self._lib, None, rc)
         self._check(self._lib.gxsv_set_option(self._h, _lib.OPT_FUSION, int(fusion)))
         self._check(self._lib.gxsv_set_option(self._h, _lib.OPT_STRICT, int(bool(strict))))
+        if batch:
+            if strict or fusion != 2:
+                raise ValueError("`batch` needs fusion=2 and strict=False")
+            self._check(self._lib.gxsv_set_option(self._h, _lib.OPT_BATCH, int(batch)))
         if vec is not None:
             self._add(vec, n)
 

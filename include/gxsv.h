@@ -53,7 +53,9 @@ enum {
                          * (default of the Python backend) */
   GXSV_OPT_STRICT = 2,  /* 1 (default) = project_qubit waits for the norm and raises like the reference */
   GXSV_OPT_PROFILE = 3, /* 1 = bracket every launch with CUDA events (read back through gxsv_stats) */
-  GXSV_OPT_DIST = 4     /* 1 = this handle is one shard of a distributed state (see the sharded section) */
+  GXSV_OPT_DIST = 4,    /* 1 = this handle is one shard of a distributed state (see the sharded section) */
+  GXSV_OPT_BATCH = 5    /* K > 0 (needs FUSION = 2, STRICT = 0): queue up to K fused projections and execute them in
+                         * ONE pass over the register; zero-norm errors surface at gxsv_sync / gxsv_flatten */
 };
 
 /* kernel kinds reported by gxsv_profile_read / gxsv_stats */

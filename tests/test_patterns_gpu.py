@@ -22,6 +22,50 @@ def test_golden_traces(name, fusion):
                     lambda cap, sel: B200StatevectorBackend.with_capacity(cap, branch_selector=sel, fusion=fusion))
 
 
+@pytest.mark.parametrize("batch", [0, 1, 3, 8])
+@pytest.mark.parametrize("name", golden_pattern_names())
+def test_golden_traces_nonstrict_batched(name, batch):
+    """strict=False: no projection waits for its norm; batch=K queues up to K fused projections and runs them as
+    ONE pass.  Outcomes are replayed without probability queries so that batches really form."""
+    d = load_golden(name)
+    holder = {}
+
+    def factory(cap, sel):
+        holder["b"] = B200StatevectorBackend.with_capacity(cap, branch_selector=sel, fusion=2, strict=False, batch=batch)
+        return holder["b"]
+
+    for trace in d["traces"]:
+        check_trace(d, trace, factory, record=False)
+        check_trace(d, trace, factory, record=True)       # probability queries force a flush before every projection
+    if batch >= 3 and name in ("rand11x6", "rand14x4", "qft13"):
+        st = holder["b"].state.stats()
+        assert st["fused"]["launches"] > 0
+
+
+def test_batched_projections_share_passes_and_defer_errors():
+    d = load_golden("rand14x4")
+    pattern = pattern_from_dict(d)
+    trace = d["traces"][0]
+    sel = mbqc.FixedBranchSelector({int(k): v for k, v in trace["outcomes"].items()})
+    launches = {}
+    for batch in (0, 8):
+        b = B200StatevectorBackend.with_capacity(pattern.max_space(), branch_selector=sel, strict=False, batch=batch)
+        PatternSimulator(pattern, b).run()
+        launches[batch] = b.state.stats()["fused"]["launches"]
+        ref = np.asarray(trace["final_state"], dtype=np.float64).view(np.complex128)
+        assert abs(np.vdot(ref, b.state.flatten())) ** 2 >= 1 - F_TOL
+    assert launches[8] * 2 < launches[0]                  # several projections per pass
+    # |0> measured along Z with outcome 1: probability 0.  strict raises in measure, non-strict at finalize.
+    p = mbqc.Pattern([], [mbqc.N(0, mbqc.BasicStates.ZERO), mbqc.N(1), mbqc.E((0, 1)), mbqc.N(2), mbqc.E((1, 2)),
+                          mbqc.M(0, mbqc.Measurement.Z), mbqc.M(1, mbqc.Measurement.XY(0.3))])
+    for kw in ({"strict": True}, {"strict": False}, {"strict": False, "batch": 4}):
+        b = B200StatevectorBackend.with_capacity(3, branch_selector=mbqc.ConstBranchSelector(1), **kw)
+        with pytest.raises(RuntimeError):
+            PatternSimulator(p, b).run()
+    with pytest.raises(ValueError):
+        B200StatevectorBackend.with_capacity(3, batch=4)   # batching needs strict=False
+
+
 @pytest.mark.parametrize("fusion", [1, 2])
 @pytest.mark.parametrize("name", ["config1_rand8x5", "qaoa7", "rand11x6"])
 def test_random_branch_same_rng_as_oracle(name, fusion):

@@ -153,7 +153,8 @@ def test_every_axis_against_oracle(n, fusion):
         np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-12)  # op is not unitary: both unnormalised alike
 
 
-@pytest.mark.parametrize("fusion,seed", [(0, 2026), (1, 2026), (2, 2026), (2, 7), (2, 8), (2, 9)])
+@pytest.mark.parametrize("fusion,seed", [(0, 2026), (1, 2026), (2, 2026), (2, 7), (2, 8), (2, 9), (-3, 7), (-8, 8), (-8, 9),
+                                         (-8, 10), (-8, 11)])
 def test_random_command_soup_against_oracle(fusion, seed):
     """Long random sequence of N / E-runs / M / 1q ops: exercises hole creation, hole filling,
     tile shifts, extent trimming, the pending-scale bookkeeping and (fusion = 2) virtual qubits,
@@ -161,7 +162,11 @@ def test_random_command_soup_against_oracle(fusion, seed):
     rng = np.random.default_rng(seed)
     n0 = 13
     psi = rand_state(rng, n0)
-    dev, orc = _sv(psi, 16, fusion=fusion), OracleStatevector(psi, max_qubits=16)
+    if fusion < 0:      # negative: lazy, non-strict, batches of -fusion projections
+        dev = _sv(psi, 16, fusion=2, strict=False, batch=-fusion)
+    else:
+        dev = _sv(psi, 16, fusion=fusion)
+    orc = OracleStatevector(psi, max_qubits=16)
     for step in range(160):
         n = orc.nqubit
         kind = rng.choice(["N", "E", "M", "U", "Z"], p=[0.25, 0.3, 0.25, 0.1, 0.1])
@@ -180,7 +185,7 @@ def test_random_command_soup_against_oracle(fusion, seed):
             vec = rng.normal(size=3)
             vec /= np.linalg.norm(vec)
             pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
-            if rng.integers(2):
+            if rng.integers(2) and (fusion >= 0 or rng.integers(3) == 0):
                 pd, po = dev.expectation_single(pm, q), orc.expectation_single(pm, q)
                 assert abs(pd - po) < 1e-10
             dev.project_qubit(pm, q)
