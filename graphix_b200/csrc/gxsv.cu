@@ -28,7 +28,7 @@ namespace {
 constexpr int HOLE_MIN = 8;     // dead bits are only ever created at physical bit >= HOLE_MIN
 constexpr int TILE_BITS = 11;   // k_contract<4,true>: a CTA tile spans the lowest 11 live bits
 constexpr int U_DEF = 4;
-constexpr int RING = 256;
+constexpr int RING = 4096;    // result slots (128 B each, pinned + mapped)
 constexpr int GXSV_VERSION = 100;
 
 struct Qubit {
@@ -1032,7 +1032,10 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
             const cplx ratio = up / ub;
             if (std::abs(ratio) > 0.0) h->hscale *= ratio / std::abs(ratio);
           }
-          if (h->deferred.size() > (size_t)(RING - 16)) { rc = check_deferred(h); if (rc) return rc; }
+          if (!h->deferred.empty() && h->seq - h->deferred.front().first > (unsigned long long)(RING - 64)) {
+            rc = check_deferred(h);   // never let the ring wrap over a result that has not been checked
+            if (rc) return rc;
+          }
           if (norms) { norms[0] = norms[1] = NAN; }
           return GXSV_OK;
         }
@@ -1061,7 +1064,10 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
         const cplx ratio = up / ub;
         if (std::abs(ratio) > 0.0) h->hscale *= ratio / std::abs(ratio);
       }
-      if (h->deferred.size() > (size_t)(RING - 16)) { rc = check_deferred(h); if (rc) return rc; }
+      if (!h->deferred.empty() && h->seq - h->deferred.front().first > (unsigned long long)(RING - 64)) {
+        rc = check_deferred(h);
+        if (rc) return rc;
+      }
       if (norms) { norms[0] = norms[1] = NAN; }
       return GXSV_OK;
     }
