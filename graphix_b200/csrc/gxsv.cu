@@ -241,12 +241,13 @@ int flush_batch(gxsv_t* h) {
   unsigned long long seq;
   Res* slot = next_slot(h, &seq);
   const int grid = grid_for(h, ngroups, 1);
+  const int fm = h->dist ? FIN_ONESHOT : FIN_BATCH;
   {
     Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
-    if (bt.naxes == 1) k_fused_batch<1><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq);
-    else if (bt.naxes == 2) k_fused_batch<2><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq);
-    else if (bt.naxes == 3) k_fused_batch<3><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq);
-    else k_fused_batch<4><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq);
+    if (bt.naxes == 1) k_fused_batch<1><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
+    else if (bt.naxes == 2) k_fused_batch<2><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
+    else if (bt.naxes == 3) k_fused_batch<3><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
+    else k_fused_batch<4><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
   }
   h->deferred.push_back({seq, bt.nstages});
   return check_launch(h, "k_fused_batch");
@@ -256,7 +257,7 @@ int flush_batch(gxsv_t* h) {
 int check_deferred(gxsv_t* h) {
   int rc = flush_batch(h);
   if (rc) return rc;
-  if (h->deferred.empty()) return GXSV_OK;
+  if (h->deferred.empty() || h->dist) return GXSV_OK;   // sharded: the caller collects the norms (gxsv_take_norms)
   std::vector<std::pair<unsigned long long, int>> todo;
   todo.swap(h->deferred);
   for (auto& d : todo) {
@@ -484,7 +485,7 @@ int launch_contract(gxsv_t* h, int qidx, cplx c0, cplx c1, uint64_t mq, unsigned
       Launch Lc(h, GXSV_K_CONTRACT, 1.5 * S);
       k_contract<U_DEF, false><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hs, p, d2(c0), d2(c1), mq, nout,
                                                            h->partials, h->ctrl, slot, seq,
-                                                           h->dist ? FIN_CONTRACT_DIST : FIN_CONTRACT);
+                                                           (h->dist ? (h->strict ? FIN_CONTRACT_DIST : FIN_ONESHOT) : FIN_CONTRACT));
     }
     h->live_mask &= ~(1ull << p);
   } else {
@@ -500,7 +501,7 @@ int launch_contract(gxsv_t* h, int qidx, cplx c0, cplx c1, uint64_t mq, unsigned
       Launch Lc(h, GXSV_K_CONTRACT, 1.5 * S);
       k_contract<U_DEF, true><<<grid, TPB, 0, h->stream>>>(h->psi, hs, hd, p, d2(c0), d2(c1), mq, nout,
                                                           h->partials, h->ctrl, slot, seq,
-                                                          h->dist ? FIN_CONTRACT_DIST : FIN_CONTRACT);
+                                                          (h->dist ? (h->strict ? FIN_CONTRACT_DIST : FIN_ONESHOT) : FIN_CONTRACT));
     }
     // qubits on L[t+1 .. K-1] slide down one live slot
     for (auto& qb : h->q) {
@@ -1012,7 +1013,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
       } else {
         const int p = h->q[q].phys;
         const cplx s0 = h->q[vi].s0, s1 = h->q[vi].s1;
-        if (h->batch_max > 0 && !h->strict && !h->dist) {
+        if (h->batch_max > 0 && !h->strict) {
           // non-strict: queue the butterfly; up to batch_max stages on <= MAX_BATCH_AXES distinct bits run as one pass
           int ax = -1;
           for (int a = 0; a < h->batch.naxes; ++a) if (h->batch.axbit[a] == p) ax = a;
@@ -1050,7 +1051,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           Launch L(h, GXSV_K_FUSED, 2.0 * state_bytes(h));
           k_fused<U_DEF><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(
               h->psi, hs, p, d2(s0 * c0), d2(s0 * c1), d2(s1 * c0), d2(-s1 * c1), mq, mv, npair, h->partials, h->ctrl,
-              slot, seq, h->dist ? FIN_CONTRACT_DIST : FIN_CONTRACT);
+              slot, seq, (h->dist ? (h->strict ? FIN_CONTRACT_DIST : FIN_ONESHOT) : FIN_CONTRACT));
         }
         rc = check_launch(h, "k_fused");
         if (rc) return rc;
@@ -1078,7 +1079,11 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
       // sharded: hand the LOCAL half-norms back; the caller all-reduces, checks and calls gxsv_set_norm.
       // Non-strict: nothing is waited for — the local norm^2 lands in the device sink, the caller all-reduces it
       // on the stream and calls gxsv_set_norm_device.
-      if (!h->strict) { if (norms) { norms[0] = norms[1] = NAN; } return GXSV_OK; }
+      if (!h->strict) {
+        h->deferred.push_back({seq, 1});
+        if (norms) { norms[0] = norms[1] = NAN; }
+        return GXSV_OK;
+      }
       rc = wait_slot(h, seq, v);
       if (rc) return rc;
       if (norms) { norms[0] = v[0] * (r0 / rbig); norms[1] = v[0] * (r1 / rbig); }
@@ -1321,6 +1326,27 @@ int gxsv_set_norm(gxsv_t* h, double total_norm2) {
   const double g = 1.0 / std::sqrt(total_norm2);
   CU(cudaMemcpyAsync(&h->ctrl->g, &g, sizeof g, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return GXSV_OK;
+}
+
+// Sharded non-blocking mode: run what is queued, wait, and hand back the local norm^2 after every projection
+// issued since the last call (in order).  The caller all-reduces them, checks them and calls gxsv_set_norm.
+int gxsv_take_norms(gxsv_t* h, double* out, int cap, int* count) {
+  CU(cudaSetDevice(h->device));
+  int rc = flush_batch(h);
+  if (rc) return rc;
+  int n = 0;
+  for (auto& d : h->deferred) {
+    double v[8];
+    rc = wait_slot(h, d.first, v);
+    if (rc) return rc;
+    for (int k = 0; k < d.second; ++k) {
+      if (n >= cap) return fail(h, GXSV_EVALUE, "take_norms: more than %d results pending", cap);
+      out[n++] = v[k];
+    }
+  }
+  h->deferred.clear();
+  *count = n;
   return GXSV_OK;
 }
 

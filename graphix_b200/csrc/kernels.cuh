@@ -98,7 +98,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* NV*8 
   }
 }
 
-enum { FIN_CONTRACT = 0, FIN_SCALED = 1, FIN_CONTRACT_DIST = 2, FIN_BATCH = 3 };
+enum { FIN_CONTRACT = 0, FIN_SCALED = 1, FIN_CONTRACT_DIST = 2, FIN_BATCH = 3, FIN_ONESHOT = 4 };
 
 // Writes the block partial, elects the last block, which sums all partials in a
 // fixed order and publishes the result to the host-mapped slot.
@@ -108,6 +108,7 @@ enum { FIN_CONTRACT = 0, FIN_SCALED = 1, FIN_CONTRACT_DIST = 2, FIN_BATCH = 3 };
 //   FIN_CONTRACT_DIST: sharded state — publish the local sum only; g is set by the host after the
 //                 all-reduce over ranks (gxsv_set_norm).
 //   FIN_BATCH    : a batch of `post` projection stages: v[k] = norm^2 after stage k; g = 1/sqrt(v[post-1]).
+//   FIN_ONESHOT  : same publication, but g <- 1 (sharded non-blocking mode: normalisation is set by the host).
 template <int NV>
 __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restrict__ partials, Ctrl* ctrl,
                                             Res* res, unsigned long long seq, int mode, double post, double g) {
@@ -144,6 +145,12 @@ __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restric
 #pragma unroll
       for (int k = 0; k < NV; ++k) res->v[k] = tot[k];
       ctrl->g = 1.0 / sqrt(tot[(int)post - 1]);
+    } else if (mode == FIN_ONESHOT) {
+      // sharded, non-blocking: publish the local norms; the pending factor g has been consumed by this pass and
+      // stays 1 until the host sets it again from the all-reduced norm (gxsv_set_norm)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) res->v[k] = tot[k];
+      ctrl->g = 1.0;
     } else {
 #pragma unroll
       for (int k = 0; k < NV; ++k) res->v[k] = tot[k] * post * g * g;
@@ -380,7 +387,7 @@ template <int A>
 __global__ void __launch_bounds__(TPB) k_fused_batch(double2* __restrict__ psi, const __grid_constant__ Holes hs,
                                                      const __grid_constant__ Batch bt, const uint64_t ngroups,
                                                      double* __restrict__ partials, Ctrl* ctrl, Res* res,
-                                                     const unsigned long long seq) {
+                                                     const unsigned long long seq, const int fin_mode) {
   constexpr int D = 1 << A;
   const double g = ctrl->g;
   uint64_t off[D];
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(TPB) k_fused_batch(double2* __restrict__ psi, 
 #pragma unroll
     for (int b = 0; b < D; ++b) st_amp(psi + base + off[b], v[b]);
   }
-  grid_finish<MAX_STAGES>(acc, partials, ctrl, res, seq, FIN_BATCH, (double)bt.nstages, g);
+  grid_finish<MAX_STAGES>(acc, partials, ctrl, res, seq, fin_mode, (double)bt.nstages, g);
 }
 
 // ---------------------------------------------------------------------------

@@ -45,8 +45,9 @@ _X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
 class GpuShardEngine:
     """The local shard: a ``B200Statevector`` in distributed mode plus torch staging buffers."""
 
-    def __init__(self, local_bits: int, device: int | None = None, strict: bool = True) -> None:
-        self.sv = B200Statevector(nqubit=0, max_qubits=local_bits, device=device, fusion=2, strict=strict)
+    def __init__(self, local_bits: int, device: int | None = None, strict: bool = True, batch: int = 8) -> None:
+        self.sv = B200Statevector(nqubit=0, max_qubits=local_bits, device=device, fusion=2, strict=strict,
+                                  batch=0 if strict else batch)
         self.sv.set_option(_lib.OPT_DIST, 1)
         self.capacity = local_bits
         self.device = torch.device("cuda", self.sv._device)
@@ -93,11 +94,17 @@ class GpuShardEngine:
     def set_norm(self, total: float) -> None:
         self.sv._check(self._lib.gxsv_set_norm(self._h, total))
 
-    def project_local_async(self, q: int, m) -> torch.Tensor:
-        """Launch the projection without waiting; returns the device tensor that will hold the local norm^2
-        of the contracted row (valid in stream order)."""
+    def project_local_async(self, q: int, m) -> None:
+        """Queue / launch the projection without waiting (consecutive fused projections share one pass)."""
         self.sv._check(self._lib.gxsv_project_qubit(self._h, q, _op8(m), 0.0, None))
-        return self.norm_buf[:1]
+
+    def take_norms(self) -> list[float]:
+        """Flush, wait, and return the local norm^2 after every projection issued since the last call."""
+        cap = 4096
+        buf = (C.c_double * cap)()
+        n = C.c_int()
+        self.sv._check(self._lib.gxsv_take_norms(self._h, buf, cap, C.byref(n)))
+        return list(buf[: n.value])
 
     def set_norm_device(self, total: torch.Tensor, scale: float) -> None:
         self.sv._check(self._lib.gxsv_set_norm_device(self._h, C.c_void_p(total.data_ptr()), scale))
@@ -155,7 +162,7 @@ class ShardedStatevector:
 
     CHUNK = 1 << 25  # amplitudes per staging buffer (512 MiB); two send + two receive buffers, allocated on demand.
     # Large on purpose: one torch.distributed batch_isend_irecv costs ~0.3 ms of host time, a 512 MiB chunk ~0.7 ms of NVLink
-    RING = 8192      # pinned slots for norms awaiting their deferred check (non-strict mode)
+    WINDOW = 64      # non-strict mode: projections between two renormalisations (one small all-reduce each)
 
     def __init__(self, engine, group=None, strict: bool | None = None) -> None:
         self.engine = engine
@@ -163,8 +170,7 @@ class ShardedStatevector:
         # strict: every projection waits for the all-reduced norm (zero-norm RuntimeError raised by the call
         # itself, like the reference).  Non-strict: nothing waits; norms are checked at the next sync point.
         self.strict = getattr(engine, "strict", True) if strict is None else strict
-        self._deferred: list[tuple[torch.Tensor, float, int]] = []
-        self._ring: torch.Tensor | None = None
+        self._window: list[tuple[float, float, int]] = []   # (weight, norm -> probability factor, qubit) per projection
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if self.P & (self.P - 1):
@@ -317,6 +323,7 @@ class ShardedStatevector:
                 self.flip[k] ^= 1
                 return
             if self.engine.nqubit == 0:
+                self._renorm()
                 self._evolve_global_scalar(qb, m)
                 return
             self._swap_in(qb)
@@ -328,6 +335,7 @@ class ShardedStatevector:
 
     def expectation_single(self, op, qubit: int) -> complex:
         qb = self._check(qubit)
+        self._renorm()
         if qb.g is not None:
             if self.engine.nqubit == 0:
                 return self._expect_global_scalar(qb, np.asarray(op, dtype=np.complex128))
@@ -346,6 +354,7 @@ class ShardedStatevector:
         qb = self._check(qubit)
         if qb.g is not None:
             if self.engine.nqubit == 0:
+                self._renorm()
                 self._project_global_scalar(qb, np.asarray(op, dtype=np.complex128))
                 return
             self._swap_in(qb)
@@ -360,20 +369,10 @@ class ShardedStatevector:
         scale = 1.0 / (1 << self._dead())
         li = qb.li
         if not self.strict:
-            # non-blocking: local norm^2 -> on-stream all-reduce -> g set on the stream; host never waits
-            t = self.engine.project_local_async(li, m)
-            if w != 1.0:
-                t.mul_(w)
-            if self.P > 1:
-                dist.all_reduce(t, group=self.group)
-            self.engine.set_norm_device(t, scale)
-            if self._ring is None:
-                self._ring = torch.empty(self.RING, dtype=torch.float64, device="cpu", pin_memory=t.is_cuda)
-            if len(self._deferred) >= self.RING:
-                self.check_deferred()
-            keep = self._ring[len(self._deferred):len(self._deferred) + 1]
-            keep.copy_(t, non_blocking=True)
-            self._deferred.append((keep, scale * (r0 + r1) / (r1 if big else r0), qubit))
+            # non-blocking: the engine queues / launches the projection (consecutive ones share a pass) and nothing
+            # waits; the norms of a whole window are all-reduced, checked and used to renormalise in _renorm()
+            self.engine.project_local_async(li, m)
+            self._window.append((w * scale, (r0 + r1) / (r1 if big else r0), qubit))
             self._remove(qb)
             for o in self.q:
                 if o.li is not None and o.li > li:
@@ -384,6 +383,8 @@ class ShardedStatevector:
                 ratio = m[0, c] / m[1, c]
                 if abs(ratio) > 0:
                     self.engine.scale_host(complex(ratio / abs(ratio)))
+            if len(self._window) >= self.WINDOW:
+                self._renorm()
             return
         n0l, n1l = self.engine.project_local(li, m)
         n0, n1 = self._allreduce([w * n0l, w * n1l])
@@ -637,19 +638,29 @@ class ShardedStatevector:
         self.engine.reset()
         self._clear()
 
-    def check_deferred(self) -> None:
-        """Non-strict mode: wait for the stream and raise the zero-norm RuntimeError of any past projection."""
-        if not self._deferred:
+    def _renorm(self) -> None:
+        """Non-strict mode: collect the local norms of the projections issued since the last call, all-reduce them,
+        raise the zero-norm RuntimeError of any of them, and set the normalisation of the current state."""
+        if not self._window:
             return
         import time  # noqa: PLC0415
 
         t0 = time.perf_counter()
-        self.engine.sync()
+        local = self.engine.take_norms()
         self.sync_wait_ms += (time.perf_counter() - t0) * 1e3
-        pending, self._deferred = self._deferred, []
-        for keep, factor, qubit in pending:
-            if float(keep[0]) * factor <= 1e-10:
+        window, self._window = self._window, []
+        if len(local) != len(window):
+            raise RuntimeError(f"sharded state: {len(local)} norms for {len(window)} projections")
+        tot = self._allreduce([wgt * n for (wgt, _, _), n in zip(window, local, strict=True)])
+        prev = 1.0                       # the window starts from a normalised state (g was set by the last _renorm)
+        for (_, factor, qubit), n in zip(window, tot, strict=True):
+            if not n * factor > 1e-10 * prev:
                 raise RuntimeError(f"Attempted to remove qubit {qubit} from 0-norm statevector (detected at sync).")
+            prev = n
+        self.engine.set_norm(tot[-1])
+
+    def check_deferred(self) -> None:
+        self._renorm()
 
     def sync(self) -> None:
         self.engine.sync()

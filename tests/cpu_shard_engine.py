@@ -17,7 +17,7 @@ class CpuShardEngine:
         self.capacity = local_bits
         self.device = torch.device("cpu")
         self.strict = strict
-        self.norm_buf = torch.zeros(2, dtype=torch.float64)
+        self._norms: list[float] = []
         self.reset()
 
     def reset(self) -> None:
@@ -124,16 +124,16 @@ class CpuShardEngine:
         self.ids.remove(i)
         return n0, n1
 
-    def project_local_async(self, q: int, m) -> torch.Tensor:
+    def project_local_async(self, q: int, m) -> None:
         m = np.asarray(m, dtype=np.complex128)
         n0, n1 = self.project_local(q, m)
         r0 = abs(m[0, 0]) ** 2 + abs(m[0, 1]) ** 2
         r1 = abs(m[1, 0]) ** 2 + abs(m[1, 1]) ** 2
-        self.norm_buf[0] = n0 if r0 >= r1 else n1
-        return self.norm_buf[:1]
+        self._norms.append(n0 if r0 >= r1 else n1)
 
-    def set_norm_device(self, total: torch.Tensor, scale: float) -> None:
-        self.set_norm(float(total[0]) * scale)
+    def take_norms(self) -> list[float]:
+        out, self._norms = self._norms, []
+        return out
 
     def set_norm(self, total: float) -> None:
         self.t = np.asarray(self.t / np.sqrt(total))
