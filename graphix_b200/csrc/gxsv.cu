@@ -44,6 +44,22 @@ struct ProfRec {
   cudaEvent_t e0, e1;
 };
 
+// A projection whose norm has not been looked at yet (non-strict mode).  The reference keeps half 0 of the
+// projected pair unless its norm is <= 1e-10 (statevec.py:1187-1190); when the larger row of the projector is row 1
+// the global phase of the result depends on that choice.  It is guessed when the projection is issued
+// (`assumed`) and corrected when the norm is finally known (`ratio` = |row0|^2 / |row1|^2, `phi` = the unit phase).
+struct StageNote {
+  double ratio = 0.0;
+  cplx phi = 1.0;
+  bool big1 = false;
+  bool assumed = false;
+};
+struct Deferred {
+  unsigned long long first = 0;   // result slot
+  int second = 0;                 // stages
+  StageNote note[8];
+};
+
 }  // namespace
 
 struct gxsv {
@@ -74,7 +90,8 @@ struct gxsv {
   int profile = 0;
   int batch_max = 0;       // > 0: queue up to this many fused projections and run them in one pass (non-strict only)
   Batch batch;             // the open batch (nstages == 0: none)
-  std::vector<std::pair<unsigned long long, int>> deferred;  // (result slot, stages) awaiting their norm check
+  std::vector<Deferred> deferred;   // projections awaiting their norm check (non-strict mode)
+  StageNote open_notes[8];          // notes of the stages in the open batch
   double* sink = nullptr;  // device slot for local norms (sharded, see gxsv_set_norm_sink)
   int dist = 0;            // sharded: projections publish local norms, the host sets g after the all-reduce
   int sm_count = 148;
@@ -249,7 +266,11 @@ int flush_batch(gxsv_t* h) {
     else if (bt.naxes == 3) k_fused_batch<3><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
     else k_fused_batch<4><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
   }
-  h->deferred.push_back({seq, bt.nstages});
+  Deferred d;
+  d.first = seq;
+  d.second = bt.nstages;
+  for (int k = 0; k < bt.nstages; ++k) d.note[k] = h->open_notes[k];
+  h->deferred.push_back(d);
   return check_launch(h, "k_fused_batch");
 }
 
@@ -258,7 +279,7 @@ int check_deferred(gxsv_t* h) {
   int rc = flush_batch(h);
   if (rc) return rc;
   if (h->deferred.empty() || h->dist) return GXSV_OK;   // sharded: the caller collects the norms (gxsv_take_norms)
-  std::vector<std::pair<unsigned long long, int>> todo;
+  std::vector<Deferred> todo;
   todo.swap(h->deferred);
   for (auto& d : todo) {
     double v[8];
@@ -266,7 +287,15 @@ int check_deferred(gxsv_t* h) {
     if (rc) return rc;
     double prev = 1.0;
     for (int k = 0; k < d.second; ++k) {
-      if (!(v[k] > 1e-10 * prev)) return fail(h, GXSV_EZERONORM, "Attempted to remove a qubit from 0-norm statevector (detected at sync).");
+      const double p = v[k] / prev;   // norm^2 of the kept (larger) row for a normalised input
+      const StageNote& nt = d.note[k];
+      const double n0 = nt.big1 ? p * nt.ratio : p, n1 = nt.big1 ? p : p * nt.ratio;
+      if (!(n0 > 1e-10) && !(n1 > 1e-10))
+        return fail(h, GXSV_EZERONORM, "Attempted to remove a qubit from 0-norm statevector (detected at sync).");
+      if (nt.big1) {
+        const bool actual = n0 > 1e-10;   // the reference would have kept half 0
+        if (actual != nt.assumed) h->hscale *= actual ? nt.phi : std::conj(nt.phi);
+      }
       prev = v[k];
     }
   }
@@ -564,6 +593,22 @@ int init_common(gxsv_t* h) {
   memset(&h->stats, 0, sizeof h->stats);
   memset(&h->batch, 0, sizeof h->batch);
   return gxsv_reset(h);
+}
+
+// Phase convention of a non-strict projection: guess which half the reference would keep, apply the phase now,
+// remember enough to correct it once the norm is known (check_deferred).
+StageNote phase_note(gxsv_t* h, int big, double r0, double r1, cplx m00, cplx m01, cplx m10, cplx m11) {
+  StageNote nt;
+  nt.big1 = (big == 1);
+  if (!nt.big1) { nt.ratio = r0 > 0.0 ? r1 / r0 : 0.0; return nt; }
+  nt.ratio = r0 / r1;
+  const cplx ub = std::abs(m10) >= std::abs(m11) ? m10 : m11;
+  const cplx up = std::abs(m10) >= std::abs(m11) ? m00 : m01;
+  const cplx ratio = up / ub;
+  nt.phi = std::abs(ratio) > 0.0 ? ratio / std::abs(ratio) : cplx(1.0);
+  nt.assumed = r0 > 1e-10 * r1;
+  if (nt.assumed && !h->dist) h->hscale *= nt.phi;   // sharded: the orchestrator owns the convention
+  return nt;
 }
 
 }  // namespace
@@ -1029,13 +1074,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           h->q[vi].phys = p;
           h->q.erase(h->q.begin() + q);
           h->hscale = 1.0;
-          if (big == 1 && r0 > 1e-10 * r1) {
-            // the reference keeps half 0 whenever its norm is above the cut-off: same phase convention
-            const cplx ub = std::abs(m10) >= std::abs(m11) ? m10 : m11;
-            const cplx up = std::abs(m10) >= std::abs(m11) ? m00 : m01;
-            const cplx ratio = up / ub;
-            if (std::abs(ratio) > 0.0) h->hscale *= ratio / std::abs(ratio);
-          }
+          h->open_notes[h->batch.nstages - 1] = phase_note(h, big, r0, r1, m00, m01, m10, m11);
           if (!h->deferred.empty() && h->seq - h->deferred.front().first > (unsigned long long)(RING - 64)) {
             rc = check_deferred(h);   // never let the ring wrap over a result that has not been checked
             if (rc) return rc;
@@ -1061,13 +1100,11 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     }
     h->hscale = 1.0;
     if (!h->strict && !h->dist) {
-      h->deferred.push_back({seq, 1});
-      if (big == 1 && r0 > 1e-10 * r1) {
-        const cplx ub = std::abs(m10) >= std::abs(m11) ? m10 : m11;
-        const cplx up = std::abs(m10) >= std::abs(m11) ? m00 : m01;
-        const cplx ratio = up / ub;
-        if (std::abs(ratio) > 0.0) h->hscale *= ratio / std::abs(ratio);
-      }
+      Deferred d;
+      d.first = seq;
+      d.second = 1;
+      d.note[0] = phase_note(h, big, r0, r1, m00, m01, m10, m11);
+      h->deferred.push_back(d);
       if (!h->deferred.empty() && h->seq - h->deferred.front().first > (unsigned long long)(RING - 64)) {
         rc = check_deferred(h);
         if (rc) return rc;
@@ -1080,7 +1117,10 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
       // Non-strict: nothing is waited for — the local norm^2 lands in the device sink, the caller all-reduces it
       // on the stream and calls gxsv_set_norm_device.
       if (!h->strict) {
-        h->deferred.push_back({seq, 1});
+        Deferred d;
+        d.first = seq;
+        d.second = 1;
+        h->deferred.push_back(d);
         if (norms) { norms[0] = norms[1] = NAN; }
         return GXSV_OK;
       }

@@ -170,7 +170,7 @@ class ShardedStatevector:
         # strict: every projection waits for the all-reduced norm (zero-norm RuntimeError raised by the call
         # itself, like the reference).  Non-strict: nothing waits; norms are checked at the next sync point.
         self.strict = getattr(engine, "strict", True) if strict is None else strict
-        self._window: list[tuple[float, float, int]] = []   # (weight, norm -> probability factor, qubit) per projection
+        self._window: list[tuple] = []   # per queued projection: (weight, big row, |row ratio|^2, phase, assumed, qubit)
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if self.P & (self.P - 1):
@@ -372,17 +372,21 @@ class ShardedStatevector:
             # non-blocking: the engine queues / launches the projection (consecutive ones share a pass) and nothing
             # waits; the norms of a whole window are all-reduced, checked and used to renormalise in _renorm()
             self.engine.project_local_async(li, m)
-            self._window.append((w * scale, (r0 + r1) / (r1 if big else r0), qubit))
+            # phase convention: the reference keeps half 0 of the projected pair unless its norm is <= 1e-10
+            # (statevec.py:1187-1190).  Guess now, correct in _renorm() once the norm is known.
+            phi, assumed = 1.0 + 0j, False
+            if big == 1:
+                c = 0 if abs(m[1, 0]) >= abs(m[1, 1]) else 1
+                ratio = m[0, c] / m[1, c]
+                phi = complex(ratio / abs(ratio)) if abs(ratio) > 0 else 1.0 + 0j
+                assumed = bool(r0 > 1e-10 * r1)
+                if assumed:
+                    self.engine.scale_host(phi)
+            self._window.append((w * scale, big, (r0 / r1) if big else (r1 / r0 if r0 > 0 else 0.0), phi, assumed, qubit))
             self._remove(qb)
             for o in self.q:
                 if o.li is not None and o.li > li:
                     o.li -= 1
-            if big == 1 and r0 > 1e-10 * r1:
-                # the reference keeps half 0 whenever its norm is above the cut-off: same phase convention
-                c = 0 if abs(m[1, 0]) >= abs(m[1, 1]) else 1
-                ratio = m[0, c] / m[1, c]
-                if abs(ratio) > 0:
-                    self.engine.scale_host(complex(ratio / abs(ratio)))
             if len(self._window) >= self.WINDOW:
                 self._renorm()
             return
@@ -651,11 +655,15 @@ class ShardedStatevector:
         window, self._window = self._window, []
         if len(local) != len(window):
             raise RuntimeError(f"sharded state: {len(local)} norms for {len(window)} projections")
-        tot = self._allreduce([wgt * n for (wgt, _, _), n in zip(window, local, strict=True)])
+        tot = self._allreduce([rec[0] * n for rec, n in zip(window, local, strict=True)])
         prev = 1.0                       # the window starts from a normalised state (g was set by the last _renorm)
-        for (_, factor, qubit), n in zip(window, tot, strict=True):
-            if not n * factor > 1e-10 * prev:
+        for (_, big, ratio, phi, assumed, qubit), n in zip(window, tot, strict=True):
+            p = n / prev                 # norm^2 of the kept (larger) row for a normalised input
+            n0, n1 = (p * ratio, p) if big else (p, p * ratio)
+            if not n0 > 1e-10 and not n1 > 1e-10:
                 raise RuntimeError(f"Attempted to remove qubit {qubit} from 0-norm statevector (detected at sync).")
+            if big and (n0 > 1e-10) != assumed:
+                self.engine.scale_host(phi if n0 > 1e-10 else phi.conjugate())
             prev = n
         self.engine.set_norm(tot[-1])
 
