@@ -235,7 +235,8 @@ def gpu_arm(args) -> None:
         def make_backend():
             # non-blocking projections: norms are all-reduced on the stream, the zero-norm check is deferred to finalize
             return ShardedStatevectorBackend.with_capacity(width, branch_selector=selector, fusion=args.fusion,
-                                                           strict=not args.nonstrict)
+                                                           strict=not args.nonstrict,
+                                                           pattern=None if args.no_schedule else pattern)
     else:
         def make_backend():
             # default: lazy fusion, non-blocking projections, up to --batch projections per pass
@@ -603,6 +604,8 @@ def main() -> None:
     ap.add_argument("--strict", dest="nonstrict", action="store_false",
                     help="wait for the norm of every projection like the reference (default: non-blocking projections, "
                          "zero-norm check deferred to finalize)")
+    ap.add_argument("--no-schedule", action="store_true",
+                    help="N > 1: do not hand the pattern's measurement order to the sharded backend (eviction heuristic only)")
     ap.add_argument("--batch", type=int, default=8, help="N = 1, non-strict: fused projections per pass (0 = one pass each)")
     ap.set_defaults(nonstrict=True)
     ap.add_argument("--cpu-window", type=int, default=0, help="commands per CPU sample (0 = auto)")

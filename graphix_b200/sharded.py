@@ -179,6 +179,7 @@ class ShardedStatevector:
         self._stage: dict[str, torch.Tensor] = {}
         self.exchanged_bytes = 0
         self.n_swaps = 0
+        self.victim_priority = None     # optional callable(logical index) -> float: larger = evict to a global bit first
         self.profile = False            # bracket every exchange with CUDA events (bench.py)
         self._xev: list[tuple] = []
         self.exchange_ms = 0.0
@@ -499,7 +500,12 @@ class ShardedStatevector:
             raise NotImplementedError("swap of a global qubit needs at least one local qubit")
         real = [o for o in locals_ if not self.engine.is_virtual(o.li)]
         pool = real if real else locals_
-        return max(pool, key=lambda o: o.li)       # the most recently added local qubit is measured last
+        if self.victim_priority is not None:
+            # the caller knows when each qubit is needed next (e.g. the measurement order of the pattern):
+            # evict the one needed farthest in the future (Belady), ties broken towards the newest qubit
+            pos = {id(o): i for i, o in enumerate(self.q)}
+            return max(pool, key=lambda o: (self.victim_priority(pos[id(o)]), o.li))
+        return max(pool, key=lambda o: o.li)       # heuristic: the most recently added local qubit is measured last
 
     def _swap_in(self, glo: _Q) -> None:
         """Swap global qubit ``glo`` with a local qubit through a pairwise half-shard exchange."""
@@ -707,14 +713,30 @@ class ShardedStatevectorBackend(B200StatevectorBackend):
 
     @classmethod
     def with_capacity(cls, max_qubits: int, state=None, *, engine=None, group=None, device: int | None = None,
-                      fusion: int = 2, strict: bool = True, **kwargs) -> "ShardedStatevectorBackend":
-        """``max_qubits`` is the TOTAL width (``Pattern.max_space()``); each rank holds ``max_qubits - log2 P`` bits."""
+                      fusion: int = 2, strict: bool = True, pattern=None, **kwargs) -> "ShardedStatevectorBackend":
+        """``max_qubits`` is the TOTAL width (``Pattern.max_space()``); each rank holds ``max_qubits - log2 P`` bits.
+
+        ``pattern`` (optional, like ``TensorNetworkBackend(pattern, ...)``, graphix/sim/tensornet.py:617-674): the
+        pattern about to be simulated.  Only its measurement ORDER is used, to decide which local qubit is parked on
+        a rank-index bit when a global qubit has to be swapped in (the one measured farthest in the future)."""
         del fusion, state
         P = dist.get_world_size(group) if dist.is_initialized() else 1
         g = P.bit_length() - 1
         if engine is None:
             engine = GpuShardEngine(max(max_qubits - g, 1), device=device, strict=strict)
-        return cls(ShardedStatevector(engine, group=group, strict=strict), **kwargs)
+        backend = cls(ShardedStatevector(engine, group=group, strict=strict), **kwargs)
+        if pattern is not None:
+            backend.use_schedule(pattern)
+        return backend
+
+    def use_schedule(self, pattern) -> None:
+        """Record when every node of ``pattern`` is measured (outputs: never) for the eviction policy."""
+        when = {}
+        for t, cmd in enumerate(pattern):
+            if cmd.kind.name == "M":
+                when[cmd.node] = t
+        ni = self.node_index
+        self.state.victim_priority = lambda pos: when.get(ni[pos], float("inf"))
 
     def measure(self, node: int, measurement, rng=None, *, stacklevel: int = 1):
         """base_backend.py:812-856 through the generic state surface."""

@@ -201,12 +201,41 @@ def case_golden_nonstrict(rank, world):
     return swaps
 
 
+def case_schedule(rank, world):
+    """with_capacity(..., pattern=p): the measurement order drives the eviction policy (Belady) -> same states,
+    fewer half-shard exchanges than the newest-qubit heuristic."""
+    from cpu_shard_engine import CpuShardEngine
+    from helpers import check_trace, load_golden
+
+    from graphix_b200.pattern_io import pattern_from_dict
+    from graphix_b200.sharded import ShardedStatevectorBackend
+
+    g = dist.get_world_size().bit_length() - 1
+    swaps = {False: 0, True: 0}
+    for name in ("rand11x6", "qft10", "qaoa7"):
+        d = load_golden(name)
+        pattern = pattern_from_dict(d)
+        for use in (False, True):
+            holder = {}
+
+            def factory(cap, sel, holder=holder, use=use):
+                holder["b"] = ShardedStatevectorBackend.with_capacity(
+                    cap, engine=CpuShardEngine(max(cap - g, 1)), branch_selector=sel, pattern=pattern if use else None)
+                return holder["b"]
+
+            for trace in d["traces"]:
+                check_trace(d, trace, factory)
+                swaps[use] += holder["b"].state.n_swaps
+    assert swaps[True] < swaps[False], swaps
+    return swaps[True]
+
+
 def case_soup_nonstrict(rank, world):
     return case_soup(rank, world, strict=False)
 
 
 CASES = {"golden": case_golden, "soup": case_soup, "random_branch": case_random_branch,
-         "golden_nonstrict": case_golden_nonstrict, "soup_nonstrict": case_soup_nonstrict}
+         "golden_nonstrict": case_golden_nonstrict, "soup_nonstrict": case_soup_nonstrict, "schedule": case_schedule}
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -226,6 +255,11 @@ def test_sharded_command_soup_vs_oracle(world):
 def test_sharded_nonstrict_command_soup(world):
     out = run_case("soup_nonstrict", world)
     assert out[0] > 0 and len(set(out.values())) == 1
+
+
+def test_sharded_schedule_hint_reduces_exchanges():
+    out = run_case("schedule", 4)
+    assert len(set(out.values())) == 1
 
 
 def test_sharded_nonstrict_deferred_norms():
