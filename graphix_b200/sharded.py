@@ -537,7 +537,9 @@ class ShardedStatevector:
         partner = self.rank ^ (1 << k)
         half = self.engine.half_size()
         factor = complex(self.u[partner] / self.u[self.rank]) if self.u[self.rank] != 0 else 1.0 + 0j
-        chunk = min(half, self.CHUNK)
+        # 8 chunks per exchange, but never below CHUNK (512 MiB: host cost of a torch P2P batch ~ its NVLink time)
+        # nor above 4 * CHUNK (2 GiB per staging buffer, four buffers)
+        chunk = min(half, max(self.CHUNK, min(half // 8, 4 * self.CHUNK)))
         # software pipeline over chunks with two staging pairs: the NVLink transfer of chunk c overlaps with
         # packing chunk c+1 and unpacking chunk c-1 (pack/unpack run on the compute stream, NCCL on its own)
         inflight: list[tuple[list, int, int, torch.Tensor]] = []
