@@ -265,7 +265,6 @@ def gpu_arm(args) -> None:
     backend.state.set_option(_lib.OPT_PROFILE, 1)
     if world > 1:
         backend.state.profile = True
-    host_t0 = time.perf_counter()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

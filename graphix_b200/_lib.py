@@ -66,8 +66,6 @@ SIGNATURES = {
     "gxsv_settle": (C.c_int, [_H, C.c_int]),
     "gxsv_set_norm": (C.c_int, [_H, C.c_double]),
     "gxsv_take_norms": (C.c_int, [_H, _D, C.c_int, _I]),
-    "gxsv_set_norm_sink": (C.c_int, [_H, C.c_void_p]),
-    "gxsv_set_norm_device": (C.c_int, [_H, C.c_void_p, C.c_double]),
     "gxsv_scale_host": (C.c_int, [_H, C.c_double, C.c_double]),
     "gxsv_get_hscale": (C.c_int, [_H, _D]),
     "gxsv_scale": (C.c_int, [_H, C.c_double, C.c_double]),

@@ -92,7 +92,6 @@ struct gxsv {
   Batch batch;             // the open batch (nstages == 0: none)
   std::vector<Deferred> deferred;   // projections awaiting their norm check (non-strict mode)
   StageNote open_notes[8];          // notes of the stages in the open batch
-  double* sink = nullptr;  // device slot for local norms (sharded, see gxsv_set_norm_sink)
   int dist = 0;            // sharded: projections publish local norms, the host sets g after the all-reduce
   int sm_count = 148;
   gxsv_stats_t stats;
@@ -700,8 +699,7 @@ int gxsv_reset(gxsv_t* h) {
   h->live_mask = 0;
   h->hscale = 1.0;
   const double2 one = make_double2(1.0, 0.0);
-  Ctrl c0 = {1.0, 0u, 0u, nullptr};
-  c0.sink = h->sink;
+  const Ctrl c0 = {1.0, 0u, 0u};
   CU(cudaMemcpyAsync(h->psi, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->ctrl, &c0, sizeof c0, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -799,7 +797,6 @@ int gxsv_tensor(gxsv_t* h, int k, const double* vec) {
     h->hscale *= cplx(s0.x, s0.y) * c.g;
     c.g = 1.0;
     c.ticket = 0;
-    c.sink = h->sink;
     CU(cudaMemcpyAsync(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->psi, vec, sizeof(double2) * nnew, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1114,8 +1111,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     }
     if (h->dist) {
       // sharded: hand the LOCAL half-norms back; the caller all-reduces, checks and calls gxsv_set_norm.
-      // Non-strict: nothing is waited for — the local norm^2 lands in the device sink, the caller all-reduces it
-      // on the stream and calls gxsv_set_norm_device.
+      // Non-strict: nothing is waited for — the caller collects the norms of a whole window (gxsv_take_norms).
       if (!h->strict) {
         Deferred d;
         d.first = seq;
@@ -1201,7 +1197,9 @@ static int gather_chunk(gxsv_t* h, double2* out, uint64_t first, uint64_t count)
 
 int gxsv_flatten_device(gxsv_t* h, void* out_device) {
   CU(cudaSetDevice(h->device));
-  int rc = flush_pending(h);
+  int rc = check_deferred(h);
+  if (rc) return rc;
+  rc = flush_pending(h);
   if (rc) return rc;
   rc = upload_tables(h);
   if (rc) return rc;
@@ -1388,21 +1386,6 @@ int gxsv_take_norms(gxsv_t* h, double* out, int cap, int* count) {
   h->deferred.clear();
   *count = n;
   return GXSV_OK;
-}
-
-int gxsv_set_norm_sink(gxsv_t* h, void* device_double) {
-  CU(cudaSetDevice(h->device));
-  h->sink = (double*)device_double;
-  CU(cudaMemcpyAsync(&h->ctrl->sink, &h->sink, sizeof(double*), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return GXSV_OK;
-}
-
-int gxsv_set_norm_device(gxsv_t* h, const void* device_total, double scale) {
-  CU(cudaSetDevice(h->device));
-  k_set_g<<<1, 1, 0, h->stream>>>(h->ctrl, (const double*)device_total, scale);
-  h->stats.launches[GXSV_K_MISC] += 1;
-  return check_launch(h, "k_set_g");
 }
 
 int gxsv_get_hscale(gxsv_t* h, double out[2]) {

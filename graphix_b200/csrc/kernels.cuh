@@ -32,7 +32,6 @@ struct Ctrl {            // device-resident control block
   double g;              // pending real normalisation: true psi = g * h(host) * stored
   unsigned int ticket;   // last-block election
   unsigned int pad;
-  double* sink;          // sharded states: device slot that receives the local norm^2 (all-reduced by the caller)
 };
 
 struct Res {             // one slot of the host-mapped result ring
@@ -140,7 +139,6 @@ __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restric
       res->v[0] = tot[0];
     } else if (mode == FIN_CONTRACT_DIST) {
       res->v[0] = tot[0];
-      if (ctrl->sink) ctrl->sink[0] = tot[0];
     } else if (mode == FIN_BATCH) {
 #pragma unroll
       for (int k = 0; k < NV; ++k) res->v[k] = tot[k];
@@ -700,11 +698,6 @@ __global__ void __launch_bounds__(TPB) k_dm_diag(const double2* __restrict__ psi
     }
   }
   grid_finish<4>(acc, partials, ctrl, res, seq, FIN_SCALED, 1.0, 1.0);
-}
-
-// g <- 1/sqrt(total * scale), total read from device memory (the all-reduced norm^2 of a sharded projection)
-__global__ void k_set_g(Ctrl* ctrl, const double* __restrict__ total, const double scale) {
-  ctrl->g = 1.0 / sqrt(total[0] * scale);
 }
 
 // ---------------------------------------------------------------------------

@@ -54,9 +54,6 @@ class GpuShardEngine:
         self._lib = self.sv._lib
         self._h = self.sv._h
         self.strict = strict
-        # device slot the projection kernels drop their local norm^2 into (non-blocking path)
-        self.norm_buf = torch.zeros(2, dtype=torch.float64, device=self.device)
-        self.sv._check(self._lib.gxsv_set_norm_sink(self._h, C.c_void_p(self.norm_buf.data_ptr())))
 
     # queries
     @property
@@ -105,9 +102,6 @@ class GpuShardEngine:
         n = C.c_int()
         self.sv._check(self._lib.gxsv_take_norms(self._h, buf, cap, C.byref(n)))
         return list(buf[: n.value])
-
-    def set_norm_device(self, total: torch.Tensor, scale: float) -> None:
-        self.sv._check(self._lib.gxsv_set_norm_device(self._h, C.c_void_p(total.data_ptr()), scale))
 
     def scale_host(self, c: complex) -> None:
         self.sv._check(self._lib.gxsv_scale_host(self._h, c.real, c.imag))

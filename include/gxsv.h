@@ -165,14 +165,10 @@ int gxsv_nreal(gxsv_t* h);                 /* materialised local qubits */
 int gxsv_is_virtual(gxsv_t* h, int q);     /* 1 = prepared but not materialised (lazy mode) */
 int gxsv_settle(gxsv_t* h, int q);         /* materialise q and issue every queued CZ touching it */
 int gxsv_set_norm(gxsv_t* h, double total_norm2);
-/* non-blocking variant: projections also write their local norm^2 to *device_double; after the caller's
- * on-stream all-reduce, gxsv_set_norm_device sets g = 1/sqrt(*device_total * scale) on the stream. */
 /* non-blocking sharded projections (STRICT = 0, optionally BATCH = K): every projection pass consumes the pending
  * factor g once and leaves g = 1; gxsv_take_norms flushes, waits and returns the local norm^2 after each projection
  * issued since the previous call, so that the caller can all-reduce, check and renormalise a whole window at once. */
 int gxsv_take_norms(gxsv_t* h, double* out, int cap, int* count);
-int gxsv_set_norm_sink(gxsv_t* h, void* device_double);
-int gxsv_set_norm_device(gxsv_t* h, const void* device_total, double scale);
 int gxsv_scale_host(gxsv_t* h, double re, double im); /* multiply the pending host scalar (no pass) */
 int gxsv_get_hscale(gxsv_t* h, double out[2]);        /* read the pending host scalar */
 int gxsv_scale(gxsv_t* h, double re, double im);      /* multiply every local amplitude (one pass) */
