@@ -382,21 +382,23 @@ struct Batch {
   Stage st[MAX_STAGES];
 };
 template <int A>
-__global__ void __launch_bounds__(TPB) k_fused_batch(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+__global__ void __launch_bounds__(TPB, (A <= 3) ? 3 : 1) k_fused_batch(double2* __restrict__ psi, const __grid_constant__ Holes hs,
                                                      const __grid_constant__ Batch bt, const uint64_t ngroups,
                                                      double* __restrict__ partials, Ctrl* ctrl, Res* res,
                                                      const unsigned long long seq, const int fin_mode) {
   constexpr int D = 1 << A;
   const double g = ctrl->g;
-  uint64_t off[D];
+  // offset of register slot b = OR of the axis bits set in b; only the A single-bit offsets are kept live
+  uint64_t ax[A];
 #pragma unroll
-  for (int b = 0; b < D; ++b) {
+  for (int a = 0; a < A; ++a) ax[a] = 1ull << bt.axbit[a];
+  auto off_of = [&](int b) {
     uint64_t o = 0;
 #pragma unroll
     for (int a = 0; a < A; ++a)
-      if ((b >> a) & 1) o |= 1ull << bt.axbit[a];
-    off[b] = o;
-  }
+      if ((b >> a) & 1) o |= ax[a];
+    return o;
+  };
   double acc[MAX_STAGES];
 #pragma unroll
   for (int k = 0; k < MAX_STAGES; ++k) acc[k] = 0.0;
@@ -404,12 +406,14 @@ __global__ void __launch_bounds__(TPB) k_fused_batch(double2* __restrict__ psi, 
     const uint64_t base = expand(j, hs);
     double2 v[D];
 #pragma unroll
-    for (int b = 0; b < D; ++b) v[b] = ld_amp(psi + base + off[b]);
+    for (int b = 0; b < D; ++b) {
+      const double2 a = ld_amp(psi + base + off_of(b));
+      v[b] = make_double2(g * a.x, g * a.y);       // the pending normalisation, once per pass
+    }
 #pragma unroll
     for (int s = 0; s < MAX_STAGES; ++s) {
       if (s < bt.nstages) {
         const Stage& st = bt.st[s];
-        const double sc = (s == 0) ? g : 1.0;
 #pragma unroll
         for (int a = 0; a < A; ++a) {
           if (st.axis == a) {
@@ -417,14 +421,14 @@ __global__ void __launch_bounds__(TPB) k_fused_batch(double2* __restrict__ psi, 
             for (int lo = 0; lo < D; ++lo) {
               if ((lo >> a) & 1) continue;
               const int hi = lo | (1 << a);
-              const uint64_t idx = base + off[lo];
-              const double sq = ((__popcll(idx & st.mq) & 1) ? -sc : sc);
-              const double sv = (__popcll(idx & st.mv) & 1) ? -1.0 : 1.0;
-              const double2 t0 = make_double2(sc * v[lo].x, sc * v[lo].y);
-              const double2 t1 = make_double2(sq * v[hi].x, sq * v[hi].y);
-              const double2 r0 = cmad2(st.m00, t0, st.m01, t1);
-              double2 r1 = cmad2(st.m10, t0, st.m11, t1);
-              r1.x *= sv; r1.y *= sv;
+              const uint64_t idx = base + off_of(lo);
+              // queued CZ signs: conditional negation, no multiplies
+              const bool nq = __popcll(idx & st.mq) & 1;
+              const bool nv = __popcll(idx & st.mv) & 1;
+              const double2 t1 = nq ? make_double2(-v[hi].x, -v[hi].y) : v[hi];
+              const double2 r0 = cmad2(st.m00, v[lo], st.m01, t1);
+              double2 r1 = cmad2(st.m10, v[lo], st.m11, t1);
+              if (nv) { r1.x = -r1.x; r1.y = -r1.y; }
               acc[s] += cnorm2(r0) + cnorm2(r1);
               v[lo] = r0;
               v[hi] = r1;
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(TPB) k_fused_batch(double2* __restrict__ psi, 
       }
     }
 #pragma unroll
-    for (int b = 0; b < D; ++b) st_amp(psi + base + off[b], v[b]);
+    for (int b = 0; b < D; ++b) st_amp(psi + base + off_of(b), v[b]);
   }
   grid_finish<MAX_STAGES>(acc, partials, ctrl, res, seq, fin_mode, (double)bt.nstages, g);
 }
