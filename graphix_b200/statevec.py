@@ -353,3 +353,20 @@ class B200Statevector:
 
     def reset_stats(self) -> None:
         self._check(self._lib.gxsv_reset_stats(self._h))
+
+
+def _register_with_graphix() -> None:
+    """When graphix is importable, make ``isinstance(state, graphix.sim.statevec.Statevector)`` (and ``DenseState``)
+    hold for ``B200Statevector`` — helper code in graphix and its tests dispatches on those classes
+    (e.g. tests/test_pattern.py:39-44).  ``Statevector`` is an ABC (via ``DenseState``), so this is a virtual
+    subclass registration: no graphix code is inherited."""
+    try:
+        from graphix.sim.base_backend import DenseState  # noqa: PLC0415
+        from graphix.sim.statevec import Statevector  # noqa: PLC0415
+    except Exception:  # noqa: BLE001 - graphix absent
+        return
+    DenseState.register(B200Statevector)
+    Statevector.register(B200Statevector)
+
+
+_register_with_graphix()
