@@ -50,6 +50,26 @@ def measured_peak() -> tuple[float, str]:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# kernel kind (gxsv_stats) -> kernel name in the committed ncu captures
+_NCU_KERNEL = {"fused": "k_fused_batch", "contract": "k_contract", "fill": "k_fill", "cz": "k_cz_star"}
+
+
+def ncu_traffic(kind: str, workload: str, batched: bool) -> float | None:
+    """DRAM bytes per launch of the dominant kernel from the ncu --set full capture committed under profiles/
+    (taken on config 2; not transferable to other workloads, hence None there)."""
+    if workload != "config2_rand26x20":
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            t = json.load(f)
+        name = _NCU_KERNEL.get(kind)
+        if kind == "fused" and not batched:
+            name = "k_fused"
+        return float(t[name]["dram_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def workload_for(n_gpus: int, name: str | None) -> str:
     if name:
         return name
@@ -399,7 +419,7 @@ def gpu_arm(args) -> None:
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / NOMINAL_HBM_GBS,
-        "traffic": None,
+        "traffic": ncu_traffic(dom, name, bool(args.nonstrict and args.batch)) if world == 1 else None,
         "algo_bytes_per_launch": d["algo_bytes"] / d["launches"], "avg_launch_ms": d["device_ms"] / d["launches"],
         "share_of_kernel_time": d["device_ms"] / total_kernel_ms,
         "all_kernels_achieved": total_bytes / (total_kernel_ms * 1e-3) / 1e9,
