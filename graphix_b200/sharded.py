@@ -154,8 +154,8 @@ class _Q:
 class ShardedStatevector:
     """State object with the reference ``Statevector`` surface over P ranks (P a power of two)."""
 
-    CHUNK = 1 << 25  # amplitudes per staging buffer (512 MiB); two send + two receive buffers, allocated on demand.
-    # Large on purpose: one torch.distributed batch_isend_irecv costs ~0.3 ms of host time, a 512 MiB chunk ~0.7 ms of NVLink
+    CHUNK_MIN = 1 << 22   # amplitudes per staging buffer: at least 64 MiB ...
+    CHUNK_MAX = 1 << 27   # ... at most 2 GiB; two send + two receive buffers, allocated on demand
     WINDOW = 64      # non-strict mode: projections between two renormalisations (one small all-reduce each)
 
     def __init__(self, engine, group=None, strict: bool | None = None) -> None:
@@ -531,9 +531,9 @@ class ShardedStatevector:
         partner = self.rank ^ (1 << k)
         half = self.engine.half_size()
         factor = complex(self.u[partner] / self.u[self.rank]) if self.u[self.rank] != 0 else 1.0 + 0j
-        # 8 chunks per exchange, but never below CHUNK (512 MiB: host cost of a torch P2P batch ~ its NVLink time)
-        # nor above 4 * CHUNK (2 GiB per staging buffer, four buffers)
-        chunk = min(half, max(self.CHUNK, min(half // 8, 4 * self.CHUNK)))
+        # 4 chunks per exchange so that packing / unpacking overlap the NVLink transfer, between 64 MiB (a torch P2P
+        # batch costs ~0.3 ms of host time, which runs ahead of the device) and 2 GiB per staging buffer (four buffers)
+        chunk = min(half, max(self.CHUNK_MIN, min(half // 4, self.CHUNK_MAX)))
         # software pipeline over chunks with two staging pairs: the NVLink transfer of chunk c overlaps with
         # packing chunk c+1 and unpacking chunk c-1 (pack/unpack run on the compute stream, NCCL on its own)
         inflight: list[tuple[list, int, int, torch.Tensor]] = []

@@ -108,7 +108,7 @@ def case_soup(rank, world, strict=True):
         if not strict:
             sh.WINDOW = 5
         if seed % 2 == 0:
-            sh.CHUNK = 4            # several chunks per exchange: exercises the double-buffered pipeline
+            sh.CHUNK_MIN = 2        # several chunks per exchange: exercises the double-buffered pipeline
         orc = OracleStatevector(nqubit=0, max_qubits=cap)
         states = [mbqc.BasicStates.PLUS, mbqc.BasicStates.MINUS, mbqc.BasicStates.ZERO, mbqc.BasicStates.ONE,
                   mbqc.PlanarState(mbqc.Plane.YZ, 0.37), mbqc.PlanarState(mbqc.Plane.XY, 1.21)]
