@@ -407,17 +407,19 @@ def gpu_arm(args) -> None:
         # end to end on N GPUs: the inputs are product states (nothing to upload), the result of every step is
         # delivered to pinned HOST memory: every rank reads back its shard of the final state
         eng = backend.state.engine
-        nloc_out = len(pattern.output_nodes) - (world.bit_length() - 1)
-        host_out = torch.empty(1 << max(nloc_out, 0), dtype=torch.complex128).pin_memory()
-        np_out = host_out.numpy()
+        np_out = None
 
         def e2e_step_sharded() -> None:
             backend.state.reset()
             backend.node_index.clear()
             PatternSimulator(pattern, backend).run()
             backend.state.check_deferred()
-            eng.sv.flatten(out=np_out[: 1 << eng.nqubit])
+            if np_out is not None:
+                eng.sv.flatten(out=np_out)
 
+        e2e_step_sharded()          # untimed: learn the size of the local shard of the output state
+        host_out = torch.empty(1 << eng.nqubit, dtype=torch.complex128).pin_memory()
+        np_out = host_out.numpy()
         e2e_step_sharded()
         barrier()
         e0.record()
