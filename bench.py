@@ -315,6 +315,17 @@ def gpu_arm(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     value = ncmd * args.steps / (dev_ms * 1e-3)
+    exchange = None
+    if world > 1:
+        st = backend.state
+        st.collect_profile()
+        exchange = {"swaps_per_step": st.n_swaps / args.steps,
+                    "nvlink_bytes_per_rank_per_step": st.exchanged_bytes / args.steps,
+                    "device_ms_per_step": st.exchange_ms / args.steps,
+                    "host_ms_per_step": st.exchange_host_ms / args.steps,
+                    "host_wait_for_device_ms_per_step": st.sync_wait_ms / args.steps,
+                    "GBps_per_direction": (st.exchanged_bytes / 1e9) / (st.exchange_ms * 1e-3) if st.exchange_ms else None}
+        st.profile = False
 
     # ---- secondary: the same pattern in the two stricter modes, same timing rules ----------
     #   per_command : fusion = 1 — one kernel per command (runs of E fused), the north_star's per-command design
@@ -489,14 +500,7 @@ def gpu_arm(args) -> None:
         "per_command": per_command, "strict_lazy": strict_lazy,
     }
     if world > 1:
-        st = backend.state
-        st.collect_profile()
-        line["exchange"] = {"swaps_per_step": st.n_swaps / args.steps,
-                            "nvlink_bytes_per_rank_per_step": st.exchanged_bytes / args.steps,
-                            "device_ms_per_step": st.exchange_ms / args.steps,
-                            "host_ms_per_step": st.exchange_host_ms / args.steps,
-                            "host_wait_for_device_ms_per_step": st.sync_wait_ms / args.steps,
-                            "GBps_per_direction": (st.exchanged_bytes / 1e9) / (st.exchange_ms * 1e-3) if st.exchange_ms else None}
+        line["exchange"] = exchange
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
