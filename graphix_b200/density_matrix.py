@@ -256,6 +256,23 @@ class B200DensityMatrix:
         self.cols = [shift(i) for i in self.cols]
         self.normalize()
 
+    def remove_qubit(self, qubit: int) -> None:
+        """Trace a qubit out and normalise — density_matrix.py:367-371 (``ptrace`` + ``normalize``).
+
+        Done with the kernels already there: one 2-axis pass moves rho_00 + rho_11 of the qubit into its |0><0| block
+        (superoperator with S[00,00] = S[00,11] = 1), then the |0><0| projection removes the qubit."""
+        q = self._q(qubit)
+        sop = np.zeros((4, 4), dtype=np.complex128)
+        sop[0, 0] = sop[0, 3] = 1.0
+        self._super(sop, [q])
+        self.project_qubit(np.array([[1, 0], [0, 0]], dtype=np.complex128), q)
+
+    def ptrace(self, qargs) -> None:
+        """density_matrix.py:373-396; the result is also normalised (the engine keeps rho at unit trace)."""
+        qs = [qargs] if isinstance(qargs, int) else sorted(qargs, reverse=True)
+        for q in qs:
+            self.remove_qubit(q)
+
     def normalize(self) -> None:
         """rho /= Tr(rho) — density_matrix.py:354-365."""
         if self.nqubit == 0:

@@ -117,6 +117,22 @@ def test_dm_soup_against_oracle():
     assert abs(dev.trace() - 1) < 1e-10
 
 
+def test_dm_remove_qubit_and_ptrace_against_oracle(g):
+    for n in (2, 3, 4):
+        rho = g[f"n{n}_rho"]
+        for q in range(n):
+            dev, orc = B200DensityMatrix(rho), OracleDensityMatrix(rho)
+            dev.remove_qubit(q)
+            orc.remove_qubit(q)
+            np.testing.assert_allclose(dev.rho, orc.rho, atol=1e-12)
+    dev, orc = B200DensityMatrix(g["n4_rho"]), OracleDensityMatrix(g["n4_rho"])
+    dev.ptrace([0, 2])
+    orc.ptrace(2)
+    orc.ptrace(0)
+    orc.normalize()
+    np.testing.assert_allclose(dev.rho, orc.rho, atol=1e-12)
+
+
 def test_dm_string_backend_noise_contract_and_fidelity():
     d = load_golden("dm_rand3x2")
     from graphix_b200.pattern_io import pattern_from_dict
