@@ -247,7 +247,12 @@ def gpu_arm(args) -> None:
         # bounded prefix window: the first --max-commands commands; whatever is alive then is the output
         pattern = mbqc.Pattern(pattern.input_nodes, list(pattern)[: args.max_commands])
     ncmd = len(pattern)
-    selector = mbqc.ConstBranchSelector(0)
+    if args.selector == "random":
+        # graphix's default: RandomBranchSelector(pr_calc=True) — every measurement first asks for its probability
+        selector = mbqc.RandomBranchSelector(pr_calc=True)
+    else:
+        selector = mbqc.ConstBranchSelector(0)
+    run_rng = (lambda: np.random.default_rng(0)) if args.selector == "random" else (lambda: None)
 
     if world > 1:
         from graphix_b200.sharded import ShardedStatevectorBackend
@@ -275,7 +280,7 @@ def gpu_arm(args) -> None:
     def one_step(profile: bool = False) -> None:
         backend.state.reset()
         backend.node_index.clear()
-        PatternSimulator(pattern, backend).run()
+        PatternSimulator(pattern, backend).run(rng=run_rng())
 
     # ---- device-resident arm -------------------------------------------------
     for _ in range(args.warmup):
@@ -490,7 +495,8 @@ def gpu_arm(args) -> None:
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "c128", "data": "synthetic",
         "config": {"workload": name, "commands_per_step": ncmd, "live_qubits": f"{width - 1}<->{width}",
-                   "state_bytes_max": 16 << (width if world == 1 else width), "selector": "ConstBranchSelector(0)",
+                   "state_bytes_max": 16 << (width if world == 1 else width),
+                   "selector": "ConstBranchSelector(0)" if args.selector != "random" else "RandomBranchSelector(pr_calc=True), rng=default_rng(0)",
                    "fusion": args.fusion, "max_commands": args.max_commands or None,
                    "strict_norm_check": not args.nonstrict, "batch": args.batch if args.nonstrict else 0,
                    "parallelism": f"shard{world}" if world > 1 else "single",
@@ -660,6 +666,8 @@ def main() -> None:
     ap.add_argument("--strict", dest="nonstrict", action="store_false",
                     help="wait for the norm of every projection like the reference (default: non-blocking projections, "
                          "zero-norm check deferred to finalize)")
+    ap.add_argument("--selector", default="const0", choices=["const0", "random"],
+                    help="const0 = ConstBranchSelector(0) (BASELINE configs); random = graphix's default selector")
     ap.add_argument("--no-schedule", action="store_true",
                     help="N > 1: do not hand the pattern's measurement order to the sharded backend (eviction heuristic only)")
     ap.add_argument("--batch", type=int, default=8, help="N = 1, non-strict: fused projections per pass (0 = one pass each)")

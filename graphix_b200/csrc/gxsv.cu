@@ -964,6 +964,58 @@ int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) 
   CU(cudaSetDevice(h->device));
   int rc = check_q(h, q);
   if (rc) return rc;
+  if (h->fusion >= 2 && h->q[q].phys >= 0) {
+    // Lazy mode, probability of a projector |v><v| (what `measure` asks for): nothing has to be materialised.
+    // Queued CZs between q and real qubits are a sign on the x_q = 1 amplitude; a queued CZ with a virtual partner in
+    // state (s0, s1) contributes the sign (-1)^a with probability |s_a|^2, so
+    //   p = w_even * sum |t0 + t1|^2 + w_odd * sum |t0 - t1|^2,   w = parity distribution of the virtual partners.
+    const cplx m00(m[0], m[1]), m01(m[2], m[3]), m10(m[4], m[5]), m11(m[6], m[7]);
+    const double r0 = std::norm(m00) + std::norm(m01), r1 = std::norm(m10) + std::norm(m11);
+    const bool herm = std::abs(m01 - std::conj(m10)) <= 1e-14 && std::abs(m00.imag()) <= 1e-14 && std::abs(m11.imag()) <= 1e-14;
+    const bool rank1 = std::abs(m00 * m11 - m01 * m10) <= 1e-13 * (r0 + r1);
+    const bool unit_trace = std::abs(m00.real() + m11.real() - 1.0) <= 1e-12;
+    if (herm && rank1 && unit_trace) {
+      dedupe_pending(h);
+      const int qid = h->q[q].id;
+      uint64_t mq = 0;
+      double w_even = 1.0, w_odd = 0.0;
+      bool ok = true;
+      for (auto& e : h->pend) {
+        if (e.first != qid && e.second != qid) continue;
+        Qubit* o = by_id(h, e.first == qid ? e.second : e.first);
+        if (o->phys >= 0) { mq |= 1ull << o->phys; continue; }
+        const double p0v = std::norm(o->s0), p1v = std::norm(o->s1);
+        if (std::abs(p0v + p1v - 1.0) > 1e-12) { ok = false; break; }
+        const double we = w_even * p0v + w_odd * p1v, wo = w_even * p1v + w_odd * p0v;
+        w_even = we;
+        w_odd = wo;
+      }
+      if (ok) {
+        const int big = (r0 >= r1) ? 0 : 1;
+        const double nb = std::sqrt(big ? r1 : r0);
+        const cplx c0 = (big ? m10 : m00) / nb, c1 = (big ? m11 : m01) / nb;   // the bra <v| up to a phase
+        const int p = h->q[q].phys;
+        const uint64_t npair = 1ull << (nlive_bits(h) - 1);
+        Holes hs = make_holes(h, p);
+        unsigned long long seq;
+        Res* slot = next_slot(h, &seq);
+        {
+          Launch L(h, GXSV_K_EXPECT, state_bytes(h));
+          k_pair_reduce<U_DEF, 2><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(
+              h->psi, hs, p, d2(c0), d2(c1), d2(0.0), d2(0.0), npair, h->partials, h->ctrl, slot, seq,
+              std::norm(h->hscale), mq);
+        }
+        rc = check_launch(h, "k_pair_reduce");
+        if (rc) return rc;
+        double v[8];
+        rc = wait_slot(h, seq, v);
+        if (rc) return rc;
+        out[0] = w_even * v[0] + w_odd * v[1];
+        out[1] = 0.0;
+        return GXSV_OK;
+      }
+    }
+  }
   rc = settle(h, q);  // CZs not touching q and virtual qubits not entangled with q do not change <op_q>
   if (rc) return rc;
   const int p = h->q[q].phys;
@@ -976,7 +1028,7 @@ int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) 
     Launch L(h, GXSV_K_EXPECT, state_bytes(h));
     k_pair_reduce<U_DEF, 0><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(
         h->psi, hs, p, make_double2(m[0], m[1]), make_double2(m[2], m[3]), make_double2(m[4], m[5]),
-        make_double2(m[6], m[7]), npair, h->partials, h->ctrl, slot, seq, std::norm(h->hscale));
+        make_double2(m[6], m[7]), npair, h->partials, h->ctrl, slot, seq, std::norm(h->hscale), 0ull);
   }
   rc = check_launch(h, "k_pair_reduce");
   if (rc) return rc;
@@ -1157,7 +1209,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     Launch L(h, GXSV_K_EXPECT, state_bytes(h));
     k_pair_reduce<U_DEF, 1><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(
         h->psi, hs, p, d2(m00), d2(m01), d2(m10), d2(m11), npair, h->partials, h->ctrl, slot, seq,
-        std::norm(h->hscale));
+        std::norm(h->hscale), 0ull);
   }
   rc = check_launch(h, "k_pair_reduce");
   if (rc) return rc;

@@ -519,6 +519,9 @@ __global__ void __launch_bounds__(TPB) k_scale_all(double2* __restrict__ psi, co
 // Reductions over pairs of axis p (read S, write nothing)
 //   WHAT 0: <psi| op |psi>            -> (re, im)          expectation_single
 //   WHAT 1: |row0 . pair|^2, |row1 . pair|^2 summed        half-norms of op|psi>
+//   WHAT 2: lazy-mode probability of a rank-1 projector <c| on a qubit that still has queued CZs: with
+//           t0 = c0 a, t1 = (-1)^{parity(x & mq)} c1 b it returns sum |t0 + t1|^2 and sum |t0 - t1|^2; the host
+//           weights the two by the parity distribution of the not-yet-materialised CZ partners.
 // ---------------------------------------------------------------------------
 template <int U, int WHAT>
 __global__ void __launch_bounds__(TPB) k_pair_reduce(const double2* __restrict__ psi,
@@ -526,17 +529,20 @@ __global__ void __launch_bounds__(TPB) k_pair_reduce(const double2* __restrict__
                                                      const double2 m00, const double2 m01, const double2 m10,
                                                      const double2 m11, const uint64_t npair,
                                                      double* __restrict__ partials, Ctrl* ctrl, Res* res,
-                                                     const unsigned long long seq, const double post) {
+                                                     const unsigned long long seq, const double post,
+                                                     const uint64_t mq) {
   const double g = ctrl->g;
   const uint64_t chunk = (uint64_t)TPB * U;
   const uint64_t poff = 1ull << pbit;
   double acc[2] = {0.0, 0.0};
   for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < npair; base += (uint64_t)gridDim.x * chunk) {
     double2 a[U], b[U];
+    bool neg[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint64_t j = base + (uint64_t)u * TPB + threadIdx.x;
       const uint64_t s = expand(j, hs);
+      neg[u] = (WHAT == 2) && (__popcll(s & mq) & 1);
       if (j < npair) {
         a[u] = ld_amp(psi + s);
         b[u] = ld_amp(psi + s + poff);
@@ -546,6 +552,14 @@ __global__ void __launch_bounds__(TPB) k_pair_reduce(const double2* __restrict__
     for (int u = 0; u < U; ++u) {
       const uint64_t j = base + (uint64_t)u * TPB + threadIdx.x;
       if (j < npair) {
+        if (WHAT == 2) {
+          const double2 t0 = cmul(m00, a[u]);
+          double2 t1 = cmul(m01, b[u]);
+          if (neg[u]) { t1.x = -t1.x; t1.y = -t1.y; }
+          acc[0] += cnorm2(make_double2(t0.x + t1.x, t0.y + t1.y));
+          acc[1] += cnorm2(make_double2(t0.x - t1.x, t0.y - t1.y));
+          continue;
+        }
         const double2 r0 = cmad2(m00, a[u], m01, b[u]);
         const double2 r1 = cmad2(m10, a[u], m11, b[u]);
         if (WHAT == 0) {
