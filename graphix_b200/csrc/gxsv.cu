@@ -258,7 +258,15 @@ int flush_batch(gxsv_t* h) {
   Res* slot = next_slot(h, &seq);
   const int grid = grid_for(h, ngroups, 1);
   const int fm = h->dist ? FIN_ONESHOT : FIN_BATCH;
-  {
+  if (bt.nstages == 1) {
+    // a batch of one (e.g. every projection is preceded by a probability query): the plain butterfly kernel is leaner
+    const Stage& st = bt.st[0];
+    const uint64_t npair = 1ull << (n - 1);
+    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
+    k_fused<U_DEF><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, bt.axbit[0], st.m00, st.m01, st.m10,
+                                                                    st.m11, st.mq, st.mv, npair, h->partials, h->ctrl,
+                                                                    slot, seq, h->dist ? FIN_ONESHOT : FIN_CONTRACT);
+  } else {
     Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
     if (bt.naxes == 1) k_fused_batch<1><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
     else if (bt.naxes == 2) k_fused_batch<2><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
