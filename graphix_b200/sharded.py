@@ -154,7 +154,8 @@ class _Q:
 class ShardedStatevector:
     """State object with the reference ``Statevector`` surface over P ranks (P a power of two)."""
 
-    CHUNK_MIN = 1 << 22   # amplitudes per staging buffer: at least 64 MiB ...
+    CHUNK_MIN = 1 << 25   # amplitudes per staging buffer: at least 512 MiB (measured: 128 MiB chunks halve the exchange
+    # rate — every torch.distributed P2P batch has a fixed cost of a few hundred microseconds on both sides) ...
     CHUNK_MAX = 1 << 27   # ... at most 2 GiB; two send + two receive buffers, allocated on demand
     WINDOW = 64      # non-strict mode: projections between two renormalisations (one small all-reduce each)
 
@@ -531,8 +532,8 @@ class ShardedStatevector:
         partner = self.rank ^ (1 << k)
         half = self.engine.half_size()
         factor = complex(self.u[partner] / self.u[self.rank]) if self.u[self.rank] != 0 else 1.0 + 0j
-        # 4 chunks per exchange so that packing / unpacking overlap the NVLink transfer, between 64 MiB (a torch P2P
-        # batch costs ~0.3 ms of host time, which runs ahead of the device) and 2 GiB per staging buffer (four buffers)
+        # large shards: 4+ chunks per exchange so that packing / unpacking overlap the NVLink transfer; chunks stay
+        # between 512 MiB and 2 GiB per staging buffer (four buffers)
         chunk = min(half, max(self.CHUNK_MIN, min(half // 4, self.CHUNK_MAX)))
         # software pipeline over chunks with two staging pairs: the NVLink transfer of chunk c overlaps with
         # packing chunk c+1 and unpacking chunk c-1 (pack/unpack run on the compute stream, NCCL on its own)
