@@ -22,11 +22,22 @@ from .mbqc import BasicStates
 _PLUS_VEC = np.array([1, 1], dtype=np.complex128) / math.sqrt(2)
 
 
-class NoiseNotSupportedError(Exception):
-    """graphix/sim/base_backend.py:324-329."""
+def _noise_error_class():
+    """graphix's own ``NoiseNotSupportedError`` when graphix is importable (so that ``except`` clauses written against
+    graphix keep working), else an equivalent local class — graphix/sim/base_backend.py:324-329."""
+    try:
+        from graphix.sim.base_backend import NoiseNotSupportedError as Ref  # noqa: PLC0415
 
-    def __str__(self) -> str:
-        return "This backend does not support noise."
+        return Ref
+    except Exception:  # noqa: BLE001 - graphix absent
+        class NoiseNotSupportedError(Exception):
+            def __str__(self) -> str:
+                return "This backend does not support noise."
+
+        return NoiseNotSupportedError
+
+
+NoiseNotSupportedError = _noise_error_class()
 
 
 def _torch_stream_and_device(device: int | None) -> tuple[int, int | None]:
