@@ -1,0 +1,55 @@
+"""Parity at BASELINE sizes, where neither the reference nor the oracle can run: size-independent properties.
+
+* config 2 (27 live qubits): the per-command kernels and the lazy batched path — each validated against the reference
+  at small widths — must produce the same 26-qubit output state (device fidelity), with unit norm.
+* config 4 family (examples/qft_with_tn.py: H on every |+> input gives |0...0>, whose QFT is |+...+>; 30 live qubits,
+  13 224 commands): the output must be |+...+> whatever branch is taken (known answer; the reference's own 10- and
+  13-qubit traces in tests/golden agree), so P(+) = 1 on every output qubit; run with pseudo-random outcomes so that the X/Z byproduct
+  corrections are exercised at full size too.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from helpers import load_golden
+
+from graphix_b200 import B200StatevectorBackend, PatternSimulator, mbqc
+from graphix_b200.pattern_io import pattern_from_dict
+
+pytestmark = pytest.mark.gpu
+
+
+class SeededOutcomes(mbqc.BranchSelector):
+    """Deterministic pseudo-random outcomes that never ask for a probability (flow patterns: every p = 1/2)."""
+
+    def __init__(self, seed: int) -> None:
+        self.rng = np.random.default_rng(seed)
+
+    def measure(self, qubit, f_expectation0, rng=None, *, stacklevel=1):
+        return int(self.rng.integers(2))
+
+
+def test_config2_per_command_vs_lazy_batched_same_state():
+    pattern = pattern_from_dict(load_golden("config2_rand26x20"))
+    states = []
+    for kw in ({"fusion": 1}, {"fusion": 2, "strict": False, "batch": 8}):
+        b = B200StatevectorBackend.with_capacity(pattern.max_space(), branch_selector=SeededOutcomes(5), **kw)
+        PatternSimulator(pattern, b).run()
+        assert b.state.nqubit == 26
+        assert abs(b.state.norm2() - 1) < 1e-10
+        states.append(b.state)
+    assert abs(states[0].fidelity(states[1]) - 1) < 1e-10
+
+
+def test_qft_pattern_known_output_at_30_live_qubits():
+    pattern = pattern_from_dict(load_golden("config4_qft29"))
+    assert pattern.max_space() == 30 and len(pattern) == 13224
+    b = B200StatevectorBackend.with_capacity(pattern.max_space(), branch_selector=SeededOutcomes(11), strict=False,
+                                             batch=8)
+    sim = PatternSimulator(pattern, b)
+    sim.run()
+    assert sum(sim.measure_method.results.values()) > 1000          # corrections really were conditional
+    plus = np.array([[0.5, 0.5], [0.5, 0.5]], dtype=np.complex128)
+    for q in range(b.state.nqubit):
+        assert abs(b.state.expectation_single(plus, q) - 1) < 1e-9, q
+    assert abs(b.state.norm2() - 1) < 1e-10
