@@ -96,6 +96,17 @@ class B200Statevector:
         self._device = 0 if dev is None else dev
         self._h = C.c_void_p()
         rc = self._lib.gxsv_create(cap, self._device, C.c_void_p(stream), C.byref(self._h))
+        if rc == _lib.GXSV_ENOMEM and fusion == 2 and cap > n and cap >= 30:
+            # Lazy fusion materialises at most max_space - 1 qubits for the (N, E, M)* streams the transpiler emits
+            # (the freshly prepared qubit takes over the measured qubit's amplitudes), so a register of half the
+            # requested size is enough unless the pattern really needs the last bit — in which case the growth
+            # fails later with the same MemoryError.  This is what lets a 34-live-qubit pattern run on one B200.
+            import warnings  # noqa: PLC0415
+
+            warnings.warn(f"2^{cap} amplitudes do not fit in device memory; allocating 2^{cap - 1} (lazy fusion "
+                          "rarely needs the last qubit)", stacklevel=2)
+            self._h = C.c_void_p()
+            rc = self._lib.gxsv_create(cap - 1, self._device, C.c_void_p(stream), C.byref(self._h))
         if rc != _lib.GXSV_OK:
             self._h = C.c_void_p()
             _lib.raise_for(self._lib, None, rc)
