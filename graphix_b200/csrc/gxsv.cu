@@ -118,9 +118,11 @@ int fail(gxsv_t* h, int code, const char* fmt, ...) {
 #define CU(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess)                                                                         \
+    if (e_ != cudaSuccess) {                                                                       \
+      cudaGetLastError(); /* clear the (non-sticky) error so that later launch checks start clean */ \
       return fail(h, e_ == cudaErrorMemoryAllocation ? GXSV_ENOMEM : GXSV_ECUDA, "%s: %s", #call, \
                   cudaGetErrorString(e_));                                                         \
+    }                                                                                              \
   } while (0)
 
 inline double2 d2(cplx z) { return make_double2(z.real(), z.imag()); }
@@ -647,6 +649,7 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
   cudaSetDevice(device);
   e = cudaMalloc(&h->psi, sizeof(double2) << max_qubits);
   if (e != cudaSuccess) {
+    cudaGetLastError();  // a failed allocation is not sticky, but it stays in the last-error slot until read
     int rc = fail(nullptr, GXSV_ENOMEM, "cudaMalloc of %.3f GiB failed: %s", std::ldexp(16.0, max_qubits - 30),
                   cudaGetErrorString(e));
     delete h;
