@@ -975,8 +975,12 @@ int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) 
   CU(cudaSetDevice(h->device));
   int rc = check_q(h, q);
   if (rc) return rc;
-  if (h->fusion >= 2 && h->q[q].phys >= 0) {
-    // Lazy mode, probability of a projector |v><v| (what `measure` asks for): nothing has to be materialised.
+  if (h->fusion >= 2 && h->q[q].phys < 0) {
+    rc = materialize(h, q);   // the measured qubit itself must exist; its CZ partners need not
+    if (rc) return rc;
+  }
+  if (h->fusion >= 2) {
+    // Lazy mode, probability of a projector |v><v| (what `measure` asks for): nothing else has to be materialised.
     // Queued CZs between q and real qubits are a sign on the x_q = 1 amplitude; a queued CZ with a virtual partner in
     // state (s0, s1) contributes the sign (-1)^a with probability |s_a|^2, so
     //   p = w_even * sum |t0 + t1|^2 + w_odd * sum |t0 - t1|^2,   w = parity distribution of the virtual partners.
@@ -1069,7 +1073,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
     const double rbig = big ? r1 : r0;
     // materialising queued qubits moves their amplitude s0 into the host scalar: settle first, read hscale after
     if (h->fusion < 2) rc = flush_pending(h);
-    else if (h->q[q].phys < 0) rc = settle(h, q);
+    else if (h->q[q].phys < 0) rc = materialize(h, (int)q);   // only q itself: its queued CZs are handled below
     if (rc) return rc;
     cplx c0 = (big ? m10 : m00) * h->hscale, c1 = (big ? m11 : m01) * h->hscale;
     if (h->fusion < 2) {
