@@ -169,7 +169,7 @@ def test_random_command_soup_against_oracle(fusion, seed):
     orc = OracleStatevector(psi, max_qubits=16)
     for step in range(160):
         n = orc.nqubit
-        kind = rng.choice(["N", "E", "M", "U", "Z"], p=[0.25, 0.3, 0.25, 0.1, 0.1])
+        kind = rng.choice(["N", "E", "M", "U", "Z", "P", "K"], p=[0.25, 0.28, 0.25, 0.08, 0.08, 0.03, 0.03])
         if kind == "N" and n < 16:
             st = [mbqc.BasicStates.PLUS, mbqc.BasicStates.ZERO, mbqc.BasicStates.ONE, mbqc.BasicStates.MINUS,
                   mbqc.PlanarState(mbqc.Plane.YZ, 0.37)][int(rng.integers(5))]
@@ -200,6 +200,22 @@ def test_random_command_soup_against_oracle(fusion, seed):
             m = [mbqc.Ops.Z, mbqc.Ops.X, mbqc.Ops.S][int(rng.integers(3))]
             dev.evolve_single(m, q)
             orc.evolve_single(m, q)
+        elif kind == "P":
+            # relabels: permute / swap with queued work and virtual qubits in flight
+            if rng.integers(2):
+                perm = [int(x) for x in rng.permutation(n)]
+                dev.permute(perm)
+                orc.permute(perm)
+            else:
+                a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+                dev.swap((a, b))
+                orc.swap((a, b))
+        elif kind == "K":
+            # 2-qubit unitary on arbitrary (possibly still virtual) qubits
+            qs = [int(x) for x in rng.choice(n, size=2, replace=False)]
+            u, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))
+            dev.evolve(u, qs)
+            orc.evolve(u, qs)
         if step % 20 == 19:
             assert dev.nqubit == orc.nqubit
             np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
