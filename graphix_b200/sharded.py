@@ -144,11 +144,14 @@ class GpuShardEngine:
 class _Q:
     """Location of one logical qubit: local engine index ``li`` or global bit ``g``."""
 
-    __slots__ = ("li", "g")
+    __slots__ = ("li", "g", "dep")
 
     def __init__(self, li: int | None = None, g: int | None = None) -> None:
         self.li = li
         self.g = g
+        # set while the qubit is a virtual product factor in the engine that a rank-dependent Z was flushed onto:
+        # mask of the rank bits its factor depends on (see _flush_local / _swap_in_impl)
+        self.dep = 0
 
 
 class ShardedStatevector:
@@ -219,6 +222,14 @@ class ShardedStatevector:
 
     def _flush_local(self, qb: _Q) -> None:
         """Apply the queued Z's of local qubit ``qb`` for real."""
+        mask = 0
+        for a, b in self.pend_lg:
+            if a is qb:
+                mask ^= 1 << b.g
+        if mask and self.engine.is_virtual(qb.li):
+            # the Z lands on a product factor that differs between ranks from now on; an exchange over one of these
+            # rank bits must materialise the qubit first (_swap_in_impl)
+            qb.dep |= mask
         if self._sigma(qb):
             self.engine.evolve_single(qb.li, _Z)
         self._drop_pending(qb)
@@ -528,10 +539,23 @@ class ShardedStatevector:
         vic = self._pick_victim(glo)
         self._flush_local(vic)
         self.engine.settle(vic.li)
+        # the halves that arrive were built with the partner's product factors: a virtual qubit whose factor depends
+        # on rank bit k has to be folded into the amplitudes before they travel
+        for o in self.q:
+            if o.li is not None and o.dep >> k & 1:
+                if self.engine.is_virtual(o.li):
+                    self.engine.settle(o.li)
+                o.dep = 0
         B = (self.rank >> k) & 1
         partner = self.rank ^ (1 << k)
         half = self.engine.half_size()
-        factor = complex(self.u[partner] / self.u[self.rank]) if self.u[self.rank] != 0 else 1.0 + 0j
+        mag = np.abs(self.u)
+        if mag.min() < 1e-100 * mag.max():
+            # a rank whose bookkeeping scalar is (numerically) zero — e.g. a global qubit projected onto |0> while
+            # every qubit was global — is about to receive amplitudes that are not: fold the scalars into the shards
+            self.engine.scale(complex(self.u[self.rank]))
+            self.u[:] = 1.0
+        factor = complex(self.u[partner] / self.u[self.rank])
         # large shards: 4+ chunks per exchange so that packing / unpacking overlap the NVLink transfer; chunks stay
         # between 512 MiB and 2 GiB per staging buffer (four buffers)
         chunk = min(half, max(self.CHUNK_MIN, min(half // 4, self.CHUNK_MAX)))

@@ -162,6 +162,11 @@ def case_soup(rank, world, strict=True):
                 np.testing.assert_allclose(sh.flatten(), orc.flatten(), atol=1e-11, err_msg=f"seed {seed} step {step}")
         np.testing.assert_allclose(sh.flatten(), orc.flatten(), atol=1e-11)
         swaps += sh.n_swaps
+    # the tight-capacity streams of the CPU (gloo) soak, including the seeds that once failed there, on the CUDA engine
+    import test_sharded_cpu  # noqa: PLC0415
+
+    swaps += test_sharded_cpu.case_soup(rank, world, strict=strict, seeds=[0, 1, 13, 16, 22],
+                                        engine_factory=lambda bits: GpuShardEngine(bits, device=rank, strict=strict))
     return swaps
 
 
