@@ -144,14 +144,11 @@ class GpuShardEngine:
 class _Q:
     """Location of one logical qubit: local engine index ``li`` or global bit ``g``."""
 
-    __slots__ = ("li", "g", "dep")
+    __slots__ = ("li", "g")
 
     def __init__(self, li: int | None = None, g: int | None = None) -> None:
         self.li = li
         self.g = g
-        # set while the qubit is a virtual product factor in the engine that a rank-dependent Z was flushed onto:
-        # mask of the rank bits its factor depends on (see _flush_local / _swap_in_impl)
-        self.dep = 0
 
 
 class ShardedStatevector:
@@ -222,14 +219,12 @@ class ShardedStatevector:
 
     def _flush_local(self, qb: _Q) -> None:
         """Apply the queued Z's of local qubit ``qb`` for real."""
-        mask = 0
-        for a, b in self.pend_lg:
-            if a is qb:
-                mask ^= 1 << b.g
-        if mask and self.engine.is_virtual(qb.li):
-            # the Z lands on a product factor that differs between ranks from now on; an exchange over one of these
-            # rank bits must materialise the qubit first (_swap_in_impl)
-            qb.dep |= mask
+        if any(a is qb for a, _ in self.pend_lg) and self.engine.is_virtual(qb.li):
+            # The Z below differs between ranks.  A qubit the engine still holds as a product factor outside the
+            # stored amplitudes must stay the same on every rank — the half-shard exchange moves stored amplitudes
+            # only, and the engine keeps part of a factor in a host scalar that has to be rank-uniform — so the
+            # qubit is materialised first (on every rank, whatever this rank's parity is).
+            self.engine.settle(qb.li)
         if self._sigma(qb):
             self.engine.evolve_single(qb.li, _Z)
         self._drop_pending(qb)
@@ -539,13 +534,6 @@ class ShardedStatevector:
         vic = self._pick_victim(glo)
         self._flush_local(vic)
         self.engine.settle(vic.li)
-        # the halves that arrive were built with the partner's product factors: a virtual qubit whose factor depends
-        # on rank bit k has to be folded into the amplitudes before they travel
-        for o in self.q:
-            if o.li is not None and o.dep >> k & 1:
-                if self.engine.is_virtual(o.li):
-                    self.engine.settle(o.li)
-                o.dep = 0
         B = (self.rank >> k) & 1
         partner = self.rank ^ (1 << k)
         half = self.engine.half_size()
