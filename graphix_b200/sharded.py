@@ -144,11 +144,12 @@ class GpuShardEngine:
 class _Q:
     """Location of one logical qubit: local engine index ``li`` or global bit ``g``."""
 
-    __slots__ = ("li", "g")
+    __slots__ = ("li", "g", "z")
 
     def __init__(self, li: int | None = None, g: int | None = None) -> None:
         self.li = li
         self.g = g
+        self.z = 0      # parity of rank-uniform Z's queued on a local qubit (X on a global qubit pushed through a CZ)
 
 
 class ShardedStatevector:
@@ -188,7 +189,6 @@ class ShardedStatevector:
         self.flip = [0] * self.gbits               # logical value of a global qubit = rank bit ^ flip
         self.u = np.ones(self.P, dtype=np.complex128)       # rank-dependent scalar of every rank's shard
         self.pend_lg: list[tuple[_Q, _Q]] = []     # queued CZ(local, global)
-        self.pend_z: dict[int, int] = {}           # queued Z on local qubits (id(_Q) -> parity)
 
     # -- helpers -----------------------------------------------------------------------
     def _eb(self, k: int, r: int | None = None) -> int:
@@ -207,14 +207,14 @@ class ShardedStatevector:
 
     def _sigma(self, qb: _Q) -> int:
         """Parity of the Z's queued on local qubit ``qb`` for this rank."""
-        s = self.pend_z.get(id(qb), 0)
+        s = qb.z
         for a, b in self.pend_lg:
             if a is qb:
                 s ^= self._eb(b.g)
         return s
 
     def _drop_pending(self, qb: _Q) -> None:
-        self.pend_z.pop(id(qb), None)
+        qb.z = 0
         self.pend_lg = [(a, b) for (a, b) in self.pend_lg if a is not qb]
 
     def _flush_local(self, qb: _Q) -> None:
@@ -321,7 +321,7 @@ class ShardedStatevector:
                 # X_k CZ_{lk} = CZ_{lk} Z_l X_k for every CZ still queued on k
                 for a, b in self.pend_lg:
                     if b is qb:
-                        self.pend_z[id(a)] = self.pend_z.get(id(a), 0) ^ 1
+                        a.z ^= 1
                 self.flip[k] ^= 1
                 return
             if self.engine.nqubit == 0:

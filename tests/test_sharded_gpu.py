@@ -165,7 +165,9 @@ def case_soup(rank, world, strict=True):
     # the tight-capacity streams of the CPU (gloo) soak, including the seeds that once failed there, on the CUDA engine
     import test_sharded_cpu  # noqa: PLC0415
 
-    swaps += test_sharded_cpu.case_soup(rank, world, strict=strict, seeds=[0, 1, 13, 16, 22],
+    nsoak = int(os.environ.get("GXSV_GPU_SOAK_SEEDS", "0"))     # longer replay on demand
+    seeds = list(range(nsoak)) if nsoak else [0, 1, 13, 16, 22]
+    swaps += test_sharded_cpu.case_soup(rank, world, strict=strict, seeds=seeds,
                                         engine_factory=lambda bits: GpuShardEngine(bits, device=rank, strict=strict))
     return swaps
 
