@@ -68,6 +68,23 @@ def _op8(op) -> C.Array:
     return (C.c_double * 8)(*a.view(np.float64).ravel())
 
 
+def ket_string(amplitudes: dict, precision: int = 4) -> str:
+    """Plain ``a|00> + b|01>`` rendering of a ``to_dict()`` result (fallback of ``B200Statevector.draw``)."""
+    if not amplitudes:
+        return "0"
+    terms = []
+    for ket, a in amplitudes.items():
+        a = complex(a)
+        if abs(a.imag) < 10.0 ** -precision * max(abs(a.real), 1e-300):
+            coeff = f"{a.real:.{precision}g}"
+        elif abs(a.real) < 10.0 ** -precision * abs(a.imag):
+            coeff = f"{a.imag:.{precision}g}i"
+        else:
+            coeff = f"({a.real:.{precision}g}{a.imag:+.{precision}g}i)"
+        terms.append(f"{coeff}|{ket}>")
+    return " + ".join(terms).replace("+ -", "- ")
+
+
 class B200Statevector:
     """complex128 statevector in B200 HBM.
 
@@ -324,6 +341,21 @@ class B200Statevector:
     def to_prob_dict(self, encoding: str = "MSB", *, rtol: float = 0.0, atol: float = 1e-8) -> dict:
         """statevec.py:642-668."""
         return self._to_dict_map(lambda x: np.abs(x) ** 2, encoding, rtol=rtol, atol=atol)
+
+    def draw(self, output=None, *, encoding: str = "MSB", max_denominator: int = 1000, atol: float = 1e-9,
+             rtol: float = 0.0, precision: int = 4) -> str:
+        """Ket-notation string — statevec.py:680-739.
+
+        Formatting is host-side pretty printing, not part of the device path: with graphix installed its own
+        ``graphix.pretty_print.statevec_to_str`` is used (it only reads ``to_dict`` from the state); without it the
+        amplitudes are printed as decimals.
+        """
+        try:
+            from graphix.pretty_print import statevec_to_str  # noqa: PLC0415
+        except ImportError:
+            return ket_string(self.to_dict(encoding, rtol=rtol, atol=atol), precision)
+        return statevec_to_str(self, output, encoding=encoding, max_denominator=max_denominator, atol=atol, rtol=rtol,
+                               precision=precision)
 
     def _to_dict_map(self, f, encoding: str, *, rtol: float, atol: float) -> dict:
         flat = self.flatten()

@@ -111,3 +111,21 @@ def test_check_runnability_errors():
     p = mbqc.Pattern([0], [mbqc.N(1), mbqc.M(0, mbqc.Measurement.X, {1})])
     with pytest.raises(ValueError):
         p.check_runnability()
+
+
+def test_ket_string_and_draw_passthrough():
+    """``B200Statevector.draw`` (statevec.py:680-739): decimal fallback, graphix's pretty printer when importable."""
+    from graphix_b200.statevec import B200Statevector, ket_string
+
+    assert ket_string({"00": 0.70710678, "01": -0.70710678j, "11": 0.5 - 0.5j}) == \
+        "0.7071|00> - 0.7071i|01> + (0.5-0.5i)|11>"
+    assert ket_string({}) == "0"
+
+    class Fake:
+        nqubit = 2
+
+        def to_dict(self, encoding="MSB", *, rtol=0.0, atol=1e-8):  # noqa: ARG002
+            return {"00": np.sqrt(0.5) + 0j, "01": np.sqrt(0.5) + 0j}
+
+    text = B200Statevector.draw(Fake())
+    assert "00" in text and "01" in text
