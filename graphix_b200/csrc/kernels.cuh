@@ -368,7 +368,9 @@ __global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const 
 // k_fused butterfly on its own axis, sign masks evaluated on the current index bits), accumulating the
 // norm^2 after every stage.  K stages cost 2 S instead of 2 K S.  Measured alternatives that did not help: 4 axes per
 // pass (227 registers, 1 CTA/SM), a software-pipelined loop prefetching the next group (122 registers, 2 CTAs/SM) and
-// a cheaper butterfly for |+> partners (u +- w; the extra branch costs more than the 8 multiplies it saves);
+// a cheaper butterfly for |+> partners (u +- w; the extra branch costs more than the 8 multiplies it saves), and
+// hoisting the sign parities out of the pair loop with sign-bit XORs instead of selects (same rate, 32 B of spills:
+// the pass is not issue bound although ncu shows the issue slots 65 % busy);
 // with 3 stages the pass runs at ~0.84 of the copy rate with the FP64 pipe ~45 % busy under the 1 kW power cap.
 // ---------------------------------------------------------------------------
 constexpr int MAX_STAGES = 8;
