@@ -4,7 +4,7 @@ Container-only tooling (needs /root/reference; no GPU here, so the amplitude eng
 oracle — what is exercised is the product's Backend host logic against graphix's real driver, commands, measurements,
 branch selectors and test expectations).  INTEGRATION.md §3 describes the same substitution on a GPU machine.
 
-    python tools/reference_conformance.py [pytest args...]
+    python tests/reference_conformance.py [pytest args...]
 """
 from __future__ import annotations
 

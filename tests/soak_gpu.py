@@ -1,4 +1,4 @@
-"""Randomised soak of libgxsv against the CPU oracle (run on a GPU box): python tools/soak_gpu.py [seconds] [first_seed]
+"""Randomised soak of libgxsv against the CPU oracle (run on a GPU box): python tests/soak_gpu.py [seconds] [first_seed]
 
 Every execution mode, registers of 0-14 qubits, every operation of the Statevector surface in random order; states are
 compared entry by entry every few steps.  Prints the first failing (mode, seed, step) or a summary."""

@@ -1,5 +1,5 @@
 """The reference's OWN test files, with its built-in name "statevector" routed to the product's backend class
-(tools/reference_conformance.py).  Runs only where /root/reference exists (the build container).  No GPU here:
+(tests/reference_conformance.py).  Runs only where /root/reference exists (the build container).  No GPU here:
 the state object under the backend is the CPU oracle, so this checks the Backend host logic — add_nodes /
 entangle_nodes / measure / correct_byproduct / apply_clifford / finalize, the BranchSelector protocol, with_capacity —
 against everything the reference's pattern, transpiler, simulator and branch-selector tests expect."""
@@ -19,7 +19,7 @@ if not os.path.isdir("/root/reference/graphix"):
 
 
 def test_reference_pattern_transpiler_simulator_selector_tests_pass_with_the_product_backend():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "reference_conformance.py")],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "reference_conformance.py")],
                          capture_output=True, text=True, timeout=1500, cwd=ROOT)
     tail = out.stdout[-2000:]
     m = re.search(r"(\d+) passed", out.stdout)
