@@ -120,6 +120,9 @@ def case_soup(rank, world, strict=True, engine_factory=None, seeds=None):
         # regressions found by the long soak: 13 (world 2) exchanges while a virtual local qubit carries a
         # rank-dependent factor; 16 (world 4) exchanges after a projection left exact zeros in the rank scalars
         seeds += [13, 16]
+    # GXSV_SOAK_MIX=gates: more single-qubit gates (relabels of rank bits, queued Z's) and fewer new qubits
+    mix = {"default": [0.3, 0.3, 0.2, 0.08, 0.08, 0.04],
+           "gates": [0.22, 0.25, 0.16, 0.16, 0.16, 0.05]}[os.environ.get("GXSV_SOAK_MIX", "default")]
     for seed in seeds:
         rng = np.random.default_rng(1000 + seed)
         cap = 7
@@ -134,7 +137,7 @@ def case_soup(rank, world, strict=True, engine_factory=None, seeds=None):
                   mbqc.PlanarState(mbqc.Plane.YZ, 0.37), mbqc.PlanarState(mbqc.Plane.XY, 1.21)]
         for step in range(150):
             n = orc.nqubit
-            kind = rng.choice(["N", "E", "M", "U", "D", "P"], p=[0.3, 0.3, 0.2, 0.08, 0.08, 0.04])
+            kind = rng.choice(["N", "E", "M", "U", "D", "P"], p=mix)
             if kind == "N" and n < cap:
                 st = states[int(rng.integers(len(states)))]
                 sh.add_nodes(1, st)
