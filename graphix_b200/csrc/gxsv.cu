@@ -15,6 +15,7 @@
 #include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -30,8 +31,11 @@ constexpr int TILE_BITS = 11;   // k_contract<4,true>: a CTA tile spans the lowe
 constexpr int U_DEF = 4;
 constexpr int RING = 4096;    // result slots (128 B each, pinned + mapped)
 constexpr int GXSV_VERSION = 100;
-constexpr int MAX_BATCH_AXES = 3;  // distinct physical bits one batched pass may act on. 4 was measured too (k_fused_batch<4>:
-// 227 registers, 0.54 ms per pass for 4 stages vs 0.40 ms for 3): FP64 issue and occupancy cancel the saved pass.
+constexpr int MAX_BATCH_AXES = 3;  // distinct physical bits one batched pass may act on (default; GXSV_BATCH_AXES=4 selects
+// k_fused_batch<4>).  Measured on config 2: 4 axes at 227 registers / 1 CTA per SM: 0.54 ms per pass; at 128 registers /
+// 2 CTAs per SM: 0.473 ms per pass (0.64 of the copy rate, latency bound, no power cap) with 313 instead of 411 passes
+// per step = +3 % commands/s; 3 axes: 0.371 ms per pass at 0.83-0.84 of the copy rate.  The default stays at the
+// variant that uses the memory system best; the 4-axis pass needs more bytes in flight than registers can hold.
 
 struct Qubit {
   int id;       // stable identity (queued CZs refer to ids: logical indices shift, tiles relocate bits)
@@ -88,6 +92,7 @@ struct gxsv {
   int fusion = 1;
   int strict = 1;
   int profile = 0;
+  int batch_axes = MAX_BATCH_AXES;   // distinct physical bits per batched pass (GXSV_BATCH_AXES=4 selects the 4-axis kernel)
   int batch_max = 0;       // > 0: queue up to this many fused projections and run them in one pass (non-strict only)
   Batch batch;             // the open batch (nstages == 0: none)
   std::vector<Deferred> deferred;   // projections awaiting their norm check (non-strict mode)
@@ -643,6 +648,10 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
   if (device < 0 || device >= ndev) return fail(h, GXSV_EVALUE, "device %d out of range [0, %d)", device, ndev);
   h = new gxsv();
   h->device = device;
+  if (const char* ax = std::getenv("GXSV_BATCH_AXES")) {   // tuning knob for the batched pass (3 or 4), see kernels.cuh
+    const int v = std::atoi(ax);
+    if (v >= 1 && v <= 4) h->batch_axes = v;
+  }
   h->stream = (cudaStream_t)stream;
   h->cap_bits = max_qubits;
   h->own_buf = true;
@@ -1126,7 +1135,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           // non-strict: queue the butterfly; up to batch_max stages on <= MAX_BATCH_AXES distinct bits run as one pass
           int ax = -1;
           for (int a = 0; a < h->batch.naxes; ++a) if (h->batch.axbit[a] == p) ax = a;
-          if (h->batch.nstages >= std::min(h->batch_max, (int)MAX_STAGES) || (ax < 0 && h->batch.naxes >= MAX_BATCH_AXES)) {
+          if (h->batch.nstages >= std::min(h->batch_max, (int)MAX_STAGES) || (ax < 0 && h->batch.naxes >= h->batch_axes)) {
             rc = flush_batch(h);
             if (rc) return rc;
             ax = -1;

@@ -387,7 +387,7 @@ struct Batch {
   Stage st[MAX_STAGES];
 };
 template <int A>
-__global__ void __launch_bounds__(TPB, (A <= 3) ? 4 : 1) k_fused_batch(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+__global__ void __launch_bounds__(TPB, (A <= 3) ? 4 : 2) k_fused_batch(double2* __restrict__ psi, const __grid_constant__ Holes hs,
                                                      const __grid_constant__ Batch bt, const uint64_t ngroups,
                                                      double* __restrict__ partials, Ctrl* ctrl, Res* res,
                                                      const unsigned long long seq, const int fin_mode) {
