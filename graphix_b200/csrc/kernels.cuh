@@ -373,7 +373,9 @@ __global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const 
 // the pass is not issue bound although ncu shows the issue slots 65 % busy), and staging the NEXT group of every
 // thread in its own shared-memory column with 16-byte cp.async.cg copies while the current group is computed (bytes in
 // flight during the FP64 phase, no extra registers: 0.418 ms per pass instead of 0.371 for 3 axes, 0.516 instead of
-// 0.473 for 4 axes — the LDGSTS path streams worse than plain 16-byte evict-first loads);
+// 0.473 for 4 axes — the LDGSTS path streams worse than plain 16-byte evict-first loads), and a 4-axis pass that keeps
+// half of every group in the thread's shared-memory column to stay at 3 CTAs per SM (80 registers, 104 B of spills:
+// 0.540 ms per pass);
 // with 3 stages the pass runs at ~0.84 of the copy rate with the FP64 pipe ~45 % busy under the 1 kW power cap.
 // ---------------------------------------------------------------------------
 constexpr int MAX_STAGES = 8;
