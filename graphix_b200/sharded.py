@@ -74,6 +74,13 @@ class GpuShardEngine:
     def add_qubit(self, s0: complex, s1: complex) -> None:
         self.sv._check(self._lib.gxsv_add_qubit(self._h, (C.c_double * 4)(s0.real, s0.imag, s1.real, s1.imag)))
 
+    def tensor(self, vec: np.ndarray) -> None:
+        """Append log2(len(vec)) qubits holding ``vec`` (first new qubit = MSB; no normalisation check: a rank's
+        slice of a joint input vector is not normalised on its own)."""
+        buf = np.ascontiguousarray(vec, dtype=np.complex128)
+        k = int(buf.size).bit_length() - 1
+        self.sv._check(self._lib.gxsv_tensor(self._h, k, buf.ctypes.data_as(C.c_void_p)))
+
     def entangle(self, a: int, b: int) -> None:
         self.sv.entangle((a, b))
 
@@ -244,7 +251,11 @@ class ShardedStatevector:
         return self.engine.capacity + self.gbits
 
     def add_nodes(self, nqubit: int, data) -> None:
-        """statevec.py:269-300 (product states; a joint 2^k vector is only accepted for k = 1)."""
+        """statevec.py:269-300: product states qubit by qubit, joint 2^k vectors sliced over the ranks."""
+        vec = self._joint_vector(nqubit, data)
+        if vec is not None:
+            self._add_vector(vec)
+            return
         states = self._states_of(nqubit, data)
         for s0, s1 in states:
             if self.engine.nqubit < self.engine.capacity:
@@ -266,6 +277,57 @@ class ShardedStatevector:
                 for r in range(self.P):
                     self.u[r] *= s1 if (r >> k) & 1 else s0
             self.q.append(qb)
+
+    @staticmethod
+    def _joint_vector(nqubit: int, data) -> np.ndarray | None:
+        """A 2^k amplitude vector (k >= 2) handed to ``add_nodes`` — statevec.py:186-205 — else None."""
+        if hasattr(data, "to_statevector_numpy"):
+            return None
+        if hasattr(data, "flatten") and hasattr(data, "nqubit") and not isinstance(data, np.ndarray):
+            vec = np.asarray(data.flatten(), dtype=np.complex128)       # a Statevector-like object
+        else:
+            if not isinstance(data, np.ndarray):
+                data = list(data)
+                if not data or hasattr(data[0], "to_statevector_numpy"):
+                    return None
+            vec = np.asarray(data, dtype=np.complex128).reshape(-1)
+        if vec.size <= 2:
+            return None
+        if vec.size & (vec.size - 1):
+            raise ValueError(f"Length of input data is not a power of two: {vec.size}.")
+        inferred = int(vec.size).bit_length() - 1
+        if nqubit is not None and nqubit != inferred:
+            raise ValueError(f"Mismatch between nqubit and inferred nqubit: {nqubit} != {inferred}.")
+        if not np.isclose(np.linalg.norm(vec), 1.0):
+            raise ValueError("Input state is not normalized.")
+        return vec
+
+    def _add_vector(self, vec: np.ndarray) -> None:
+        """Tensor a joint vector of k new qubits onto the state.  The last qubits go to the shard while it has room,
+        the first ones take free rank bits: every rank keeps the slice of ``vec`` that its rank bits select."""
+        k = int(vec.size).bit_length() - 1
+        kl = min(k, self.engine.capacity - self.engine.nqubit)
+        kg = k - kl
+        free = [b for b in range(self.gbits) if self.owner[b] is None]
+        if kg > len(free):
+            raise MemoryError(f"sharded state is full: {self.max_qubits} qubits")
+        new_q = []
+        t = 0
+        for i in range(kg):
+            b = free[i]
+            qb = _Q(g=b)
+            self.owner[b] = qb
+            self.flip[b] = 0
+            t = (t << 1) | ((self.rank >> b) & 1)
+            new_q.append(qb)
+        mine = vec.reshape(1 << kg, 1 << kl)[t]
+        first = self.engine.nqubit
+        if kl:
+            self.engine.tensor(mine)
+            new_q.extend(_Q(li=first + j) for j in range(kl))
+        else:
+            self.engine.scale(complex(mine[0]))      # may be exactly zero: it cannot live in the bookkeeping scalar
+        self.q.extend(new_q)
 
     @staticmethod
     def _states_of(nqubit: int, data) -> list[tuple[complex, complex]]:

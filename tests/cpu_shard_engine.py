@@ -83,6 +83,17 @@ class CpuShardEngine:
         self.virt[self._next] = [s0, s1]
         self._next += 1
 
+    def tensor(self, vec) -> None:
+        vec = np.asarray(vec, dtype=np.complex128).reshape(-1)
+        k = int(vec.size).bit_length() - 1
+        assert self.nqubit + k <= self.capacity
+        self._all()
+        self.t = np.multiply.outer(self.t, vec.reshape((2,) * k))
+        for _ in range(k):
+            self.ids.append(self._next)
+            self.real.append(self._next)
+            self._next += 1
+
     def entangle(self, a: int, b: int) -> None:
         ia, ib = self.ids[a], self.ids[b]
         if ia in self.virt or ib in self.virt:

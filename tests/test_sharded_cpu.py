@@ -87,8 +87,6 @@ def case_golden(rank, world, strict=True):
     for name in ("config1_rand8x5", "micro_prob", "handbuilt_allkinds", "qaoa7", "qft10", "rand11x6"):
         d = load_golden(name)
         for trace in d["traces"]:
-            if trace["input"]["kind"] == "vector":
-                continue
             holder = {}
 
             def factory(cap, sel, holder=holder):
@@ -182,6 +180,67 @@ def case_soup(rank, world, strict=True, engine_factory=None, seeds=None):
     return swaps
 
 
+def case_vector_inputs(rank, world, engine_factory=None):
+    """Joint 2^k input vectors (statevec.py:186-205) tensored onto partly filled sharded states: the slices that land
+    on rank bits, the ones that fill the shard, exact zeros in a rank's slice; then commands on top."""
+    from graphix_b200 import mbqc
+    from oracle.oracle import OracleStatevector, outcome_to_operator_matrix
+
+    from cpu_shard_engine import CpuShardEngine
+    from graphix_b200.sharded import ShardedStatevector
+
+    g = world.bit_length() - 1
+    cap = 7
+    for seed in range(10):
+        rng = np.random.default_rng(7000 + seed)
+        engine = CpuShardEngine(cap - g) if engine_factory is None else engine_factory(cap - g)
+        sh = ShardedStatevector(engine, strict=True)
+        orc = OracleStatevector(nqubit=0, max_qubits=cap)
+        for _ in range(int(rng.integers(0, 4))):
+            st = [mbqc.BasicStates.PLUS, mbqc.BasicStates.ONE, mbqc.PlanarState(mbqc.Plane.YZ, 0.37)][int(rng.integers(3))]
+            sh.add_nodes(1, st)
+            orc.add_nodes(1, st)
+        if orc.nqubit >= 2:
+            sh.entangle((0, 1))
+            orc.entangle((0, 1))
+        k = int(rng.integers(2, cap - orc.nqubit + 1))
+        vec = rng.normal(size=1 << k) + 1j * rng.normal(size=1 << k)
+        if seed % 3 == 0:
+            vec[: 1 << (k - 1)] = 0.0          # first new qubit in |1>: exact zeros in some ranks' slices
+        vec /= np.linalg.norm(vec)
+        sh.add_nodes(k, vec if seed % 2 else list(vec))
+        orc.add_nodes(k, vec)
+        assert sh.nqubit == orc.nqubit
+        np.testing.assert_allclose(sh.flatten(), orc.flatten(), atol=1e-12, err_msg=f"seed {seed} after add")
+        for step in range(30):
+            n = orc.nqubit
+            kind = rng.choice(["E", "M", "U"], p=[0.5, 0.3, 0.2])
+            if kind == "E" and n >= 2:
+                a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+                sh.entangle((a, b))
+                orc.entangle((a, b))
+            elif kind == "M" and n >= 2:
+                q = int(rng.integers(n))
+                v3 = rng.normal(size=3)
+                v3 /= np.linalg.norm(v3)
+                pm = outcome_to_operator_matrix(v3, int(rng.integers(2)))
+                po = orc.expectation_single(pm, q)
+                assert abs(sh.expectation_single(pm, q) - po) < 1e-10, (seed, step)
+                if po.real > 1e-6:
+                    sh.project_qubit(pm, q)
+                    orc.project_qubit(pm, q)
+            elif kind == "U" and n >= 1:
+                q = int(rng.integers(n))
+                m = mbqc.Clifford(int(rng.integers(24))).matrix
+                sh.evolve_single(m, q)
+                orc.evolve_single(m, q)
+        np.testing.assert_allclose(sh.flatten(), orc.flatten(), atol=1e-11, err_msg=f"seed {seed} end")
+    with pytest.raises(ValueError, match="not normalized"):
+        ShardedStatevector(CpuShardEngine(cap - g) if engine_factory is None else engine_factory(cap - g)).add_nodes(
+            2, np.ones(4))
+    return 0
+
+
 def case_random_branch(rank, world):
     """Every rank must take the same branch: probabilities are all-reduced, the rng is seeded identically."""
     from helpers import load_golden
@@ -257,7 +316,7 @@ def case_soup_nonstrict(rank, world):
     return case_soup(rank, world, strict=False)
 
 
-CASES = {"golden": case_golden, "soup": case_soup, "random_branch": case_random_branch,
+CASES = {"golden": case_golden, "soup": case_soup, "vector_inputs": case_vector_inputs, "random_branch": case_random_branch,
          "golden_nonstrict": case_golden_nonstrict, "soup_nonstrict": case_soup_nonstrict, "schedule": case_schedule}
 
 
@@ -272,6 +331,11 @@ def test_sharded_golden_traces(world):
 def test_sharded_command_soup_vs_oracle(world):
     out = run_case("soup", world)
     assert out[0] > 0 and len(set(out.values())) == 1
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_joint_vector_inputs(world):
+    run_case("vector_inputs", world)
 
 
 @pytest.mark.parametrize("world", [2, 4])

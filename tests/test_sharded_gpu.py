@@ -69,8 +69,6 @@ def case_golden_nonstrict(rank, world):
     for name in ("config1_rand8x5", "handbuilt_allkinds", "qaoa7", "qft10", "rand11x6", "rand14x4", "qft13"):
         d = load_golden(name)
         for trace in d["traces"]:
-            if trace["input"]["kind"] == "vector":
-                continue
             holder = {}
 
             def factory(cap, sel, holder=holder):
@@ -92,8 +90,6 @@ def case_golden(rank, world):
     for name in ("config1_rand8x5", "micro_prob", "handbuilt_allkinds", "qaoa7", "qft10", "rand11x6", "rand14x4", "qft13"):
         d = load_golden(name)
         for trace in d["traces"]:
-            if trace["input"]["kind"] == "vector":
-                continue
             holder = {}
 
             def factory(cap, sel, holder=holder):
@@ -172,6 +168,16 @@ def case_soup(rank, world, strict=True):
     return swaps
 
 
+def case_vector_inputs(rank, world):
+    """Joint input vectors sliced over the ranks: the streams of tests/test_sharded_cpu.py on the CUDA engine."""
+    import test_sharded_cpu  # noqa: PLC0415
+
+    from graphix_b200.sharded import GpuShardEngine
+
+    return test_sharded_cpu.case_vector_inputs(rank, world,
+                                               engine_factory=lambda bits: GpuShardEngine(bits, device=rank))
+
+
 def case_vs_single_gpu(rank, world):
     """rand20x5 (21 live qubits): sharded over `world` GPUs vs one GPU, same selector -> same state."""
     from helpers import load_golden
@@ -193,7 +199,8 @@ def case_vs_single_gpu(rank, world):
 
 
 CASES = {"golden": case_golden, "soup": case_soup, "vs_single": case_vs_single_gpu,
-         "golden_nonstrict": case_golden_nonstrict, "soup_nonstrict": case_soup_nonstrict}
+         "golden_nonstrict": case_golden_nonstrict, "soup_nonstrict": case_soup_nonstrict,
+         "vector_inputs": case_vector_inputs}
 
 
 def test_sharded_single_rank_runs_the_distributed_engine_mode():
@@ -206,11 +213,10 @@ def test_sharded_single_rank_runs_the_distributed_engine_mode():
     for name in ("config1_rand8x5", "micro_prob", "handbuilt_allkinds", "qaoa7", "rand11x6"):
         d = load_golden(name)
         for trace in d["traces"]:
-            if trace["input"]["kind"] == "vector":
-                continue
             check_trace(d, trace, lambda cap, sel: ShardedStatevectorBackend.with_capacity(cap, branch_selector=sel, device=0))
     assert case_soup(0, 1) == 0
     assert case_soup(0, 1, strict=False) == 0
+    assert case_vector_inputs(0, 1) == 0
     assert case_golden_nonstrict(0, 1) == 0
 
 
@@ -231,6 +237,12 @@ def test_sharded_gpu_soup(world):
     _need(world)
     out = run_case("soup", world)
     assert len(set(out.values())) == 1 and out[0] > 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_gpu_joint_vector_inputs(world):
+    _need(world)
+    run_case("vector_inputs", world)
 
 
 @pytest.mark.parametrize("world", [2, 4])
