@@ -714,6 +714,42 @@ class ShardedStatevector:
     def apply_noise(self, qubits, noise) -> None:  # noqa: ARG002
         raise NoiseNotSupportedError
 
+    def tensor(self, other) -> None:
+        """statevec.py:508-524: self <- self (x) other (``other`` is read through ``flatten()``)."""
+        vec = np.asarray(other.flatten(), dtype=np.complex128)
+        if vec.size == 1:
+            self.engine.scale_host(complex(vec[0]))
+        elif vec.size == 2:
+            self.add_nodes(1, vec)
+        else:
+            self._add_vector(vec)
+
+    def remove_qubit(self, qubit: int) -> None:
+        """statevec.py:417-428."""
+        raise NotImplementedError("This method is deprecated. See :meth:`self.project_qubit`.")
+
+    def evolve(self, op, qubits) -> None:
+        """statevec.py:361-395.  Only ``Circuit.simulate`` uses multi-qubit operators; pattern
+        simulation never does, and the sharded state does not implement them."""
+        if len(qubits) == 1:
+            self.evolve_single(op, qubits[0])
+            return
+        raise NotImplementedError("multi-qubit operators are not part of the sharded pattern-simulation path; "
+                                  "use B200Statevector.evolve on one GPU")
+
+    def expectation_value(self, op, qubits) -> complex:
+        """statevec.py:397-415 (single-qubit operators only, see :meth:`evolve`)."""
+        if len(qubits) == 1:
+            return self.expectation_single(op, qubits[0])
+        raise NotImplementedError("multi-qubit operators are not part of the sharded pattern-simulation path; "
+                                  "use B200Statevector.expectation_value on one GPU")
+
+    # read-outs through flatten() (<= 28 qubits), shared with the single-GPU state object — statevec.py:590-739
+    to_dict = B200Statevector.to_dict
+    to_prob_dict = B200Statevector.to_prob_dict
+    _to_dict_map = B200Statevector._to_dict_map
+    draw = B200Statevector.draw
+
     def reset(self) -> None:
         self.check_deferred()
         self.engine.reset()

@@ -235,6 +235,27 @@ def case_vector_inputs(rank, world, engine_factory=None):
                 sh.evolve_single(m, q)
                 orc.evolve_single(m, q)
         np.testing.assert_allclose(sh.flatten(), orc.flatten(), atol=1e-11, err_msg=f"seed {seed} end")
+        # tensor() with another state object, then the dictionary read-outs (statevec.py:508-524, 590-668)
+        if orc.nqubit <= cap - 2:
+            other = OracleStatevector(nqubit=0, max_qubits=2)
+            w = rng.normal(size=4) + 1j * rng.normal(size=4)
+            other.add_nodes(2, w / np.linalg.norm(w))
+            sh.tensor(other)
+            orc.tensor(other)
+            np.testing.assert_allclose(sh.flatten(), orc.flatten(), atol=1e-11, err_msg=f"seed {seed} tensor")
+        flat = orc.flatten()
+        got = sh.to_dict()
+        keep = [i for i in range(flat.size) if abs(flat[i]) > 1e-8]
+        assert sorted(got) == sorted(format(i, f"0{orc.nqubit}b") for i in keep)
+        for i in keep:
+            assert abs(got[format(i, f"0{orc.nqubit}b")] - flat[i]) < 1e-11
+        probs = sh.to_prob_dict(encoding="LSB")
+        assert abs(sum(probs.values()) - 1.0) < 1e-9
+        assert isinstance(sh.draw(), str)
+        with pytest.raises(NotImplementedError):
+            sh.remove_qubit(0)
+        with pytest.raises(NotImplementedError):
+            sh.evolve(np.eye(4), [0, 1])
     with pytest.raises(ValueError, match="not normalized"):
         ShardedStatevector(CpuShardEngine(cap - g) if engine_factory is None else engine_factory(cap - g)).add_nodes(
             2, np.ones(4))
