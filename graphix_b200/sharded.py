@@ -700,6 +700,25 @@ class ShardedStatevector:
             full[idx] = np.transpose(shards[r].reshape((2,) * nloc), local_axes) if nloc else shards[r][0]
         return full.reshape(1 << n)
 
+    def shard(self) -> np.ndarray:
+        """This rank's amplitudes (host copy): the sub-vector selected by this rank's bits of the global qubits, local
+        qubits in logical order (first = MSB).  ``layout()`` names the location of every logical qubit and
+        ``rank_bit_values()`` the values this rank holds for the global ones; no communication."""
+        self.check_deferred()
+        for o in self.q:
+            if o.li is not None:
+                self._flush_local(o)
+        local = np.asarray(self.engine.flatten_local(), dtype=np.complex128) * self.u[self.rank]
+        nloc = self.engine.nqubit
+        if nloc == 0:
+            return local.reshape(1)
+        local_axes = [o.li for o in self.q if o.li is not None]
+        return np.ascontiguousarray(np.transpose(local.reshape((2,) * nloc), local_axes)).reshape(-1)
+
+    def rank_bit_values(self) -> dict[int, int]:
+        """Logical index -> value (0/1) that this rank holds for every qubit living on a rank bit."""
+        return {i: self._eb(o.g) for i, o in enumerate(self.q) if o.g is not None}
+
     @property
     def psi(self) -> np.ndarray:
         return self.flatten()

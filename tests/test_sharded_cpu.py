@@ -244,6 +244,11 @@ def case_vector_inputs(rank, world, engine_factory=None):
             orc.tensor(other)
             np.testing.assert_allclose(sh.flatten(), orc.flatten(), atol=1e-11, err_msg=f"seed {seed} tensor")
         flat = orc.flatten()
+        # shard(): this rank's slice of the oracle vector, selected by rank_bit_values()
+        fixed = sh.rank_bit_values()
+        idx = tuple(fixed.get(i, slice(None)) for i in range(orc.nqubit))
+        np.testing.assert_allclose(sh.shard(), flat.reshape((2,) * orc.nqubit)[idx].reshape(-1), atol=1e-11,
+                                   err_msg=f"seed {seed} shard")
         got = sh.to_dict()
         keep = [i for i in range(flat.size) if abs(flat[i]) > 1e-8]
         assert sorted(got) == sorted(format(i, f"0{orc.nqubit}b") for i in keep)
