@@ -31,11 +31,11 @@ constexpr int TILE_BITS = 11;   // k_contract<4,true>: a CTA tile spans the lowe
 constexpr int U_DEF = 4;
 constexpr int RING = 4096;    // result slots (128 B each, pinned + mapped)
 constexpr int GXSV_VERSION = 100;
-constexpr int MAX_BATCH_AXES = 3;  // distinct physical bits one batched pass may act on (default; GXSV_BATCH_AXES=4 selects
-// k_fused_batch<4>).  Measured on config 2: 4 axes at 227 registers / 1 CTA per SM: 0.54 ms per pass; at 128 registers /
-// 2 CTAs per SM: 0.473 ms per pass (0.64 of the copy rate, latency bound, no power cap) with 313 instead of 411 passes
-// per step = +3 % commands/s; 3 axes: 0.371 ms per pass at 0.83-0.84 of the copy rate.  The default stays at the
-// variant that uses the memory system best; the 4-axis pass needs more bytes in flight than registers can hold.
+constexpr int MAX_BATCH_AXES = 5;  // distinct physical bits one batched pass may act on (GXSV_BATCH_AXES = 1..6).
+// Up to 3 axes run in k_fused_batch (2^3 amplitudes per thread in registers, 4 CTAs per SM); 4..6 axes run in
+// k_fused_tile, which keeps three axes at a time in registers and transposes the CTA tile through shared memory
+// between phases.  (Round 1 measured a 4-axis all-register pass: 128 registers, 2 CTAs per SM, 0.64 of the copy rate.)
+constexpr int DEFAULT_CHUNK_LOG2 = 3;   // consecutive 256-group blocks / tiles a CTA takes at a time (GXSV_CHUNK_LOG2)
 
 struct Qubit {
   int id;       // stable identity (queued CZs refer to ids: logical indices shift, tiles relocate bits)
@@ -92,7 +92,10 @@ struct gxsv {
   int fusion = 1;
   int strict = 1;
   int profile = 0;
-  int batch_axes = MAX_BATCH_AXES;   // distinct physical bits per batched pass (GXSV_BATCH_AXES=4 selects the 4-axis kernel)
+  int batch_axes = MAX_BATCH_AXES;   // distinct physical bits per batched pass (GXSV_BATCH_AXES)
+  int chunk_log2 = DEFAULT_CHUNK_LOG2;
+  int use_tma = 0;         // 1: batched passes stage CTA tiles through shared memory with bulk copies (k_fused_tma; measured slower for many
+                           // stages per pass, see kernels.cuh) when the layout allows
   int batch_max = 0;       // > 0: queue up to this many fused projections and run them in one pass (non-strict only)
   Batch batch;             // the open batch (nstages == 0: none)
   std::vector<Deferred> deferred;   // projections awaiting their norm check (non-strict mode)
@@ -178,6 +181,8 @@ cudaEvent_t get_event(gxsv_t* h) {
 }
 
 int flush_batch(gxsv_t* h);
+thread_local TmaBatch g_tma;        // scratch of flush_batch (kernel parameters are copied at launch)
+thread_local Holes g_tma_holes;
 
 struct Launch {
   gxsv_t* h;
@@ -246,7 +251,140 @@ int check_launch(gxsv_t* h, const char* what) {
   return GXSV_OK;
 }
 
-// Run the queued projection stages (k_fused_batch).  The layout bookkeeping was done when they were queued.
+// bit lo of the result = parity of (the physical bits of the register axes selected by lo) & mask
+unsigned char parity_table(uint64_t mask, const unsigned char* regbit, int nb) {
+  unsigned int t = 0;
+  for (int lo = 0; lo < (1 << nb); ++lo) {
+    int par = 0;
+    for (int i = 0; i < nb; ++i)
+      if (((lo >> i) & 1) && ((mask >> regbit[i]) & 1ull)) par ^= 1;
+    t |= (unsigned int)par << lo;
+  }
+  return (unsigned char)t;
+}
+
+// Greedy phase plan of a batch on more than three axes: every phase is the longest run of consecutive stages that
+// acts on at most three distinct batch axes (those are held in registers, k_fused_tile).  Returns the number of
+// phases (out may be NULL: the queueing code only asks whether one more stage still fits MAX_PHASES).
+int plan_phases(const Batch& bt, TileBatch* out) {
+  int nph = 0;
+  int i = 0;
+  while (i < bt.nstages) {
+    int T[3], nt = 0, j = i;
+    for (; j < bt.nstages; ++j) {
+      const int a = bt.st[j].axis;
+      bool in = false;
+      for (int k = 0; k < nt; ++k) in = in || (T[k] == a);
+      if (in) continue;
+      if (nt == 3) break;
+      T[nt++] = a;
+    }
+    if (out && nph < MAX_PHASES) {
+      // pad the register set to three axes with batch axes that the phase does not use
+      for (int a = 0; a < bt.naxes && nt < 3; ++a) {
+        bool in = false;
+        for (int k = 0; k < nt; ++k) in = in || (T[k] == a);
+        if (!in) T[nt++] = a;
+      }
+      std::sort(T, T + 3);
+      Phase& ph = out->ph[nph];
+      int no = 0;
+      for (int a = 0; a < bt.naxes; ++a) {
+        int slot = -1;
+        for (int k = 0; k < 3; ++k) if (T[k] == a) slot = k;
+        if (slot >= 0) ph.ax[slot] = (unsigned char)a; else ph.oth[no++] = (unsigned char)a;
+      }
+      for (; no < 3; ++no) ph.oth[no] = 0;
+      ph.s_begin = (unsigned char)i;
+      ph.s_end = (unsigned char)j;
+      unsigned char regbit[3];
+      for (int k = 0; k < 3; ++k) regbit[k] = bt.axbit[T[k]];
+      for (int s = i; s < j; ++s) {
+        for (int k = 0; k < 3; ++k) if (T[k] == bt.st[s].axis) out->lax[s] = (unsigned char)k;
+        out->st[s].qtab = parity_table(bt.st[s].mq, regbit, 3);
+        out->st[s].vtab = parity_table(bt.st[s].mv, regbit, 3);
+      }
+    }
+    nph += 1;
+    i = j;
+  }
+  return nph;
+}
+
+// Plan of the bulk-copy staged pass (k_fused_tma): tile geometry (L low physical bits + the H batch axes above them),
+// greedy phases with their three register bits given as tile-index bits, parity tables.  Returns false when the
+// layout does not allow it (fewer than 11 live bits, a dead bit inside the contiguous runs, too many phases).
+bool plan_tma(const gxsv_t* h, const Batch& bt, TmaBatch* out, Holes* hs) {
+  const int n = nlive_bits(h);
+  if (n < TILE_LOG2) return false;
+  int L = 5;
+  for (; L <= TILE_LOG2; ++L) {
+    int c = 0;
+    for (int a = 0; a < bt.naxes; ++a) c += (bt.axbit[a] >= L) ? 1 : 0;
+    if (L + c == TILE_LOG2) break;
+  }
+  if (L > TILE_LOG2) return false;
+  if ((~h->live_mask) & ((1ull << L) - 1ull)) return false;      // a dead bit would break the contiguous runs
+  memset(out, 0, sizeof *out);
+  out->L = L;
+  out->H = TILE_LOG2 - L;
+  out->nstages = bt.nstages;
+  int hb[8], nh = 0;
+  for (int a = 0; a < bt.naxes; ++a) if (bt.axbit[a] >= L) hb[nh++] = bt.axbit[a];
+  std::sort(hb, hb + nh);
+  for (int i = 0; i < nh; ++i) out->hbit[i] = (unsigned char)hb[i];
+  auto tile_bit = [&](int a) {          // tile-index bit of batch axis a
+    const int pb = bt.axbit[a];
+    if (pb < L) return pb;
+    for (int i = 0; i < nh; ++i) if (hb[i] == pb) return L + i;
+    return -1;
+  };
+  auto phys_of = [&](int sbit) { return sbit < L ? sbit : hb[sbit - L]; };
+  int nph = 0, i = 0;
+  while (i < bt.nstages) {
+    if (nph == MAX_PHASES) return false;
+    int T[3], nt = 0, j = i;
+    for (; j < bt.nstages; ++j) {
+      const int sbit = tile_bit(bt.st[j].axis);
+      bool in = false;
+      for (int k = 0; k < nt; ++k) in = in || (T[k] == sbit);
+      if (in) continue;
+      if (nt == 3) break;
+      T[nt++] = sbit;
+    }
+    for (int sbit = TILE_LOG2 - 1; sbit >= 0 && nt < 3; --sbit) {   // pad with the highest free tile-index bits
+      bool in = false;
+      for (int k = 0; k < nt; ++k) in = in || (T[k] == sbit);
+      if (!in) T[nt++] = sbit;
+    }
+    std::sort(T, T + 3);
+    unsigned char regbit[3];
+    for (int k = 0; k < 3; ++k) { out->sb[nph][k] = (unsigned char)T[k]; regbit[k] = (unsigned char)phys_of(T[k]); }
+    out->s_begin[nph] = (unsigned char)i;
+    out->s_end[nph] = (unsigned char)j;
+    for (int s2 = i; s2 < j; ++s2) {
+      out->st[s2] = bt.st[s2];
+      out->nscale[s2] = bt.nscale[s2];
+      const int sbit = tile_bit(bt.st[s2].axis);
+      for (int k = 0; k < 3; ++k) if (T[k] == sbit) out->lax[s2] = (unsigned char)k;
+      out->st[s2].qtab = parity_table(bt.st[s2].mq, regbit, 3);
+      out->st[s2].vtab = parity_table(bt.st[s2].mv, regbit, 3);
+    }
+    nph += 1;
+    i = j;
+  }
+  out->nphases = nph;
+  // tiles are enumerated over the live bits at / above L that are not batch axes
+  hs->n = 0;
+  for (int b = L; b < h->phys_bits; ++b) {
+    bool skip = !((h->live_mask >> b) & 1ull);
+    for (int k = 0; k < nh; ++k) skip = skip || (hb[k] == b);
+    if (skip) hs->pos[hs->n++] = (unsigned char)b;
+  }
+  return true;
+}
+
+// Run the queued projection stages (k_fused_batch / k_fused_tile).  The layout bookkeeping was done when they were queued.
 int flush_batch(gxsv_t* h) {
   if (h->batch.nstages == 0) return GXSV_OK;
   Batch bt = h->batch;
@@ -269,16 +407,62 @@ int flush_batch(gxsv_t* h) {
     // a batch of one (e.g. every projection is preceded by a probability query): the plain butterfly kernel is leaner
     const Stage& st = bt.st[0];
     const uint64_t npair = 1ull << (n - 1);
+    // the host scalar already holds the factor f taken out of a kind 0 / 1 stage: hand k_fused the matrix without it
+    double2 m00 = st.m00, m01 = st.m01, m10 = st.m10, m11 = st.m11;
+    if (st.kind != 2) {
+      const double rho = st.neg ? -1.0 : 1.0;
+      const double2 one = make_double2(1.0, 0.0), ra = make_double2(rho * st.a.x, rho * st.a.y);
+      if (st.kind == 0) { m00 = one; m01 = st.a; m10 = make_double2(rho, 0.0); m11 = make_double2(-ra.x, -ra.y); }
+      else { m00 = st.a; m01 = one; m10 = ra; m11 = make_double2(-rho, 0.0); }
+    }
     Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
-    k_fused<U_DEF><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, bt.axbit[0], st.m00, st.m01, st.m10,
-                                                                    st.m11, st.mq, st.mv, npair, h->partials, h->ctrl,
-                                                                    slot, seq, h->dist ? FIN_ONESHOT : FIN_CONTRACT);
+    k_fused<U_DEF><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, bt.axbit[0], m00, m01, m10, m11, st.mq,
+                                                                    st.mv, npair, h->partials, h->ctrl, slot, seq,
+                                                                    h->dist ? FIN_ONESHOT : FIN_CONTRACT, bt.nscale[0]);
+  } else if (h->use_tma && plan_tma(h, bt, &g_tma, &g_tma_holes)) {
+    const uint64_t ntiles = 1ull << (n - TILE_LOG2);
+    const size_t dyn = (sizeof(double2) << TILE_LOG2) * TMA_BUFS;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU(cudaFuncSetAttribute(k_fused_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      attr_set = true;
+    }
+    const uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * 2);   // persistent: 2 resident CTAs per SM
+    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
+    k_fused_tma<<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, g_tma_holes, g_tma, ntiles, h->partials, h->ctrl, slot, seq, fm);
+  } else if (bt.naxes <= 3) {
+    for (int k = 0; k < bt.nstages; ++k) {
+      bt.st[k].qtab = parity_table(bt.st[k].mq, bt.axbit, bt.naxes);
+      bt.st[k].vtab = parity_table(bt.st[k].mv, bt.axbit, bt.naxes);
+    }
+    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
+    // chunked CTA -> index mapping only when every CTA still gets >= 8 chunks (else plain grid stride)
+    int gl = h->chunk_log2;
+    while (gl > 0 && (ngroups >> (8 + gl)) < (uint64_t)grid * 8) --gl;
+    if (bt.naxes == 1) k_fused_batch<1><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, gl, h->partials, h->ctrl, slot, seq, fm);
+    else if (bt.naxes == 2) k_fused_batch<2><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, gl, h->partials, h->ctrl, slot, seq, fm);
+    else k_fused_batch<3><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, gl, h->partials, h->ctrl, slot, seq, fm);
   } else {
+    static thread_local TileBatch tb;
+    memset(&tb, 0, sizeof tb);
+    tb.nstages = bt.nstages;
+    tb.naxes = bt.naxes;
+    for (int a = 0; a < bt.naxes; ++a) tb.axbit[a] = bt.axbit[a];
+    for (int k = 0; k < bt.nstages; ++k) { tb.st[k] = bt.st[k]; tb.nscale[k] = bt.nscale[k]; }
+    tb.nphases = plan_phases(bt, &tb);
+    if (tb.nphases > MAX_PHASES) return fail(h, GXSV_EVALUE, "internal: batch needs %d phases", tb.nphases);
+    const uint64_t ntiles = 1ull << (n - TILE_LOG2);
+    const size_t dyn = sizeof(double2) << TILE_LOG2;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU(cudaFuncSetAttribute(k_fused_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      attr_set = true;
+    }
+    uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * 4);   // persistent: 4 resident CTAs per SM
+    int gl = h->chunk_log2;
+    while (gl > 0 && (ntiles >> gl) < tgrid * 8) --gl;
     Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
-    if (bt.naxes == 1) k_fused_batch<1><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
-    else if (bt.naxes == 2) k_fused_batch<2><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
-    else if (bt.naxes == 3) k_fused_batch<3><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
-    else k_fused_batch<4><<<grid, TPB, 0, h->stream>>>(h->psi, hs, bt, ngroups, h->partials, h->ctrl, slot, seq, fm);
+    k_fused_tile<<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm);
   }
   Deferred d;
   d.first = seq;
@@ -650,7 +834,12 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
   h->device = device;
   if (const char* ax = std::getenv("GXSV_BATCH_AXES")) {   // tuning knob for the batched pass (3 or 4), see kernels.cuh
     const int v = std::atoi(ax);
-    if (v >= 1 && v <= 4) h->batch_axes = v;
+    if (v >= 1 && v <= MAX_TILE_AXES) h->batch_axes = v;
+  }
+  if (const char* tm = std::getenv("GXSV_TMA")) h->use_tma = std::atoi(tm) ? 1 : 0;
+  if (const char* cl = std::getenv("GXSV_CHUNK_LOG2")) {
+    const int v = std::atoi(cl);
+    if (v >= 0 && v <= 10) h->chunk_log2 = v;
   }
   h->stream = (cudaStream_t)stream;
   h->cap_bits = max_qubits;
@@ -747,6 +936,18 @@ int gxsv_set_option(gxsv_t* h, int key, int value) {
       { int rc = flush_batch(h); if (rc) return rc; }
       h->batch_max = value;
       return GXSV_OK;
+    case GXSV_OPT_BATCH_AXES:
+      if (value < 1 || value > MAX_TILE_AXES) return fail(h, GXSV_EVALUE, "batch axes must be in [1, %d]", (int)MAX_TILE_AXES);
+      { int rc = flush_batch(h); if (rc) return rc; }
+      h->batch_axes = value;
+      return GXSV_OK;
+    case GXSV_OPT_CHUNK_LOG2:
+      if (value < 0 || value > 10) return fail(h, GXSV_EVALUE, "chunk log2 must be in [0, 10]");
+      h->chunk_log2 = value;
+      return GXSV_OK;
+    case GXSV_OPT_TMA:
+      h->use_tma = value ? 1 : 0;
+      return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -758,6 +959,9 @@ int gxsv_get_option(gxsv_t* h, int key, int* value) {
     case GXSV_OPT_PROFILE: *value = h->profile; return GXSV_OK;
     case GXSV_OPT_DIST: *value = h->dist; return GXSV_OK;
     case GXSV_OPT_BATCH: *value = h->batch_max; return GXSV_OK;
+    case GXSV_OPT_BATCH_AXES: *value = h->batch_axes; return GXSV_OK;
+    case GXSV_OPT_CHUNK_LOG2: *value = h->chunk_log2; return GXSV_OK;
+    case GXSV_OPT_TMA: *value = h->use_tma; return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -1135,7 +1339,18 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           // non-strict: queue the butterfly; up to batch_max stages on <= MAX_BATCH_AXES distinct bits run as one pass
           int ax = -1;
           for (int a = 0; a < h->batch.naxes; ++a) if (h->batch.axbit[a] == p) ax = a;
-          if (h->batch.nstages >= std::min(h->batch_max, (int)MAX_STAGES) || (ax < 0 && h->batch.naxes >= h->batch_axes)) {
+          // more than three axes need a CTA tile of 2^11 amplitudes (k_fused_tile)
+          const int max_axes = (nlive_bits(h) >= TILE_LOG2 + 1) ? h->batch_axes : std::min(h->batch_axes, 3);
+          bool full = h->batch.nstages >= std::min(h->batch_max, (int)MAX_STAGES) || (ax < 0 && h->batch.naxes >= max_axes);
+          if (!full && h->batch.naxes + (ax < 0 ? 1 : 0) > 3) {
+            // would the batch with this stage still fit MAX_PHASES register phases?
+            Batch& b = h->batch;
+            b.st[b.nstages].axis = (ax < 0) ? b.naxes : ax;
+            b.nstages += 1;
+            full = plan_phases(b, nullptr) > MAX_PHASES;
+            b.nstages -= 1;
+          }
+          if (full) {
             rc = flush_batch(h);
             if (rc) return rc;
             ax = -1;
@@ -1143,10 +1358,29 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           if (ax < 0) { ax = h->batch.naxes++; h->batch.axbit[ax] = (unsigned char)p; }
           Stage& st = h->batch.st[h->batch.nstages++];
           st.m00 = d2(s0 * c0); st.m01 = d2(s0 * c1); st.m10 = d2(s1 * c0); st.m11 = d2(-s1 * c1);
-          st.mq = mq; st.mv = mv; st.axis = ax; st.pad = 0;
+          st.mq = mq; st.mv = mv; st.axis = ax; st.qtab = st.vtab = 0;
+          // |+> / |-> partners (s1 = +-s0): take the scalar f = s0 * c_pivot out of the stage (Stage kinds 0 / 1 in
+          // kernels.cuh).  Its phase (sharded: f itself, so that the all-reduced norms stay those of the true state)
+          // stays in the host scalar, |f|^2 goes into the published norms.  A sharded state may carry a rank-dependent
+          // sign on c1, and the host scalar must be rank uniform: there only c0 is ever taken out.
+          const bool same = (s1 == s0), opp = (s1 == -s0);
+          const int pivot = (std::abs(c0) >= std::abs(c1)) ? 0 : 1;
+          const bool fast = (same || opp) && std::abs(s0) > 0.0 && !(h->dist && pivot == 1);
+          cplx f = 1.0;
+          st.kind = 2;
+          st.neg = 0;
+          st.a = d2(0.0);
+          if (fast) {
+            f = s0 * (pivot ? c1 : c0);
+            st.a = d2(pivot ? c0 / c1 : c1 / c0);
+            st.kind = (unsigned char)pivot;
+            st.neg = opp ? 1 : 0;
+          }
+          const int k = h->batch.nstages - 1;
+          h->batch.nscale[k] = ((k > 0 && !h->dist) ? h->batch.nscale[k - 1] : 1.0) * std::norm(f);
           h->q[vi].phys = p;
           h->q.erase(h->q.begin() + q);
-          h->hscale = 1.0;
+          h->hscale = fast ? (h->dist ? f : f / std::abs(f)) : cplx(1.0);
           h->open_notes[h->batch.nstages - 1] = phase_note(h, big, r0, r1, m00, m01, m10, m11);
           if (!h->deferred.empty() && h->seq - h->deferred.front().first > (unsigned long long)(RING - 64)) {
             rc = check_deferred(h);   // never let the ring wrap over a result that has not been checked
@@ -1163,7 +1397,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           Launch L(h, GXSV_K_FUSED, 2.0 * state_bytes(h));
           k_fused<U_DEF><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(
               h->psi, hs, p, d2(s0 * c0), d2(s0 * c1), d2(s1 * c0), d2(-s1 * c1), mq, mv, npair, h->partials, h->ctrl,
-              slot, seq, (h->dist ? (h->strict ? FIN_CONTRACT_DIST : FIN_ONESHOT) : FIN_CONTRACT));
+              slot, seq, (h->dist ? (h->strict ? FIN_CONTRACT_DIST : FIN_ONESHOT) : FIN_CONTRACT), 1.0);
         }
         rc = check_launch(h, "k_fused");
         if (rc) return rc;
@@ -1437,7 +1671,13 @@ int gxsv_settle(gxsv_t* h, int q) {
 int gxsv_set_norm(gxsv_t* h, double total_norm2) {
   CU(cudaSetDevice(h->device));
   if (!(total_norm2 > 0.0)) return fail(h, GXSV_EZERONORM, "set_norm: non-positive norm");
-  const double g = 1.0 / std::sqrt(total_norm2);
+  // total_norm2 is the norm^2 of hscale * stored over all ranks; the modulus of the host scalar moves into g so that
+  // neither drifts (batched stages leave their scalar factors in hscale, see gxsv_project_qubit)
+  // (non-blocking sharded mode only: there total_norm2 is by construction the norm^2 of hscale * stored)
+  const bool fold = h->dist && !h->strict && std::abs(h->hscale) > 0.0;
+  const double habs = fold ? std::abs(h->hscale) : 1.0;
+  const double g = habs / std::sqrt(total_norm2);
+  if (fold) h->hscale /= habs;
   CU(cudaMemcpyAsync(&h->ctrl->g, &g, sizeof g, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return GXSV_OK;

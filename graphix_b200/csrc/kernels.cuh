@@ -110,7 +110,8 @@ enum { FIN_CONTRACT = 0, FIN_SCALED = 1, FIN_CONTRACT_DIST = 2, FIN_BATCH = 3, F
 //   FIN_ONESHOT  : same publication, but g <- 1 (sharded non-blocking mode: normalisation is set by the host).
 template <int NV>
 __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restrict__ partials, Ctrl* ctrl,
-                                            Res* res, unsigned long long seq, int mode, double post, double g) {
+                                            Res* res, unsigned long long seq, int mode, double post, double g,
+                                            const double* nscale = nullptr) {
   __shared__ double red[NV * 8];
   __shared__ bool is_last;
   block_sum<NV>(acc, red);
@@ -136,18 +137,20 @@ __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restric
     ctrl->ticket = 0;
     if (mode == FIN_CONTRACT) {
       ctrl->g = 1.0 / sqrt(tot[0]);
-      res->v[0] = tot[0];
+      res->v[0] = tot[0] * (nscale ? nscale[0] : 1.0);
     } else if (mode == FIN_CONTRACT_DIST) {
       res->v[0] = tot[0];
     } else if (mode == FIN_BATCH) {
+      // stages may keep a scalar f out of the stored amplitudes (Stage kinds 0 / 1): the published norms are those of
+      // the unfactored state, g normalises what is stored
 #pragma unroll
-      for (int k = 0; k < NV; ++k) res->v[k] = tot[k];
+      for (int k = 0; k < NV; ++k) res->v[k] = tot[k] * (nscale ? nscale[k] : 1.0);
       ctrl->g = 1.0 / sqrt(tot[(int)post - 1]);
     } else if (mode == FIN_ONESHOT) {
       // sharded, non-blocking: publish the local norms; the pending factor g has been consumed by this pass and
       // stays 1 until the host sets it again from the all-reduced norm (gxsv_set_norm)
 #pragma unroll
-      for (int k = 0; k < NV; ++k) res->v[k] = tot[k];
+      for (int k = 0; k < NV; ++k) res->v[k] = tot[k] * (nscale ? nscale[k] : 1.0);
       ctrl->g = 1.0;
     } else {
 #pragma unroll
@@ -324,7 +327,8 @@ __global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const 
                                                const int pbit, double2 m00, double2 m01, double2 m10, double2 m11,
                                                const uint64_t mq, const uint64_t mv, const uint64_t npair,
                                                double* __restrict__ partials, Ctrl* ctrl, Res* res,
-                                               const unsigned long long seq, const int fin_mode) {
+                                               const unsigned long long seq, const int fin_mode,
+                                               const double nscale0) {
   const double g = ctrl->g;
   m00.x *= g; m00.y *= g; m01.x *= g; m01.y *= g; m10.x *= g; m10.y *= g; m11.x *= g; m11.y *= g;
   const uint64_t chunk = (uint64_t)TPB * U;
@@ -358,7 +362,8 @@ __global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const 
       }
     }
   }
-  grid_finish<1>(acc, partials, ctrl, res, seq, fin_mode, 1.0, g);
+  const double ns[1] = {nscale0};   // the matrix may have a scalar taken out (a batch of one, see Stage): published norm *= |f|^2
+  grid_finish<1>(acc, partials, ctrl, res, seq, fin_mode, 1.0, g, ns);
 }
 
 // ---------------------------------------------------------------------------
@@ -379,23 +384,105 @@ __global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const 
 // with 3 stages the pass runs at ~0.84 of the copy rate with the FP64 pipe ~45 % busy under the 1 kW power cap.
 // ---------------------------------------------------------------------------
 constexpr int MAX_STAGES = 8;
+// One fused (N, E.., M) stage on one axis.  With <c| the measurement bra (host scalar folded in), (s0, s1) the state of
+// the partner v and sq / sv the CZ signs of the measured qubit / of v (k_fused above):
+//   r0 = s0 (c0 t0 + c1 t1),   r1 = sv s1 (c0 t0 - c1 t1),      t0 = psi[.., 0], t1 = sq psi[.., 1].
+// kind 2 (general): the four products are in m00..m11 and the stage costs two complex 2-term dot products.
+// kind 0 / 1 (s1 = +-s0, every |+> / |-> partner): the scalar f = s0 c0 (kind 0, |c0| >= |c1|) or f = s0 c1 (kind 1) is
+//   taken out of the stage — the host keeps its phase, the published norms are multiplied by |f|^2 (Batch::nscale) — so that
+//   r0 = t0 + a t1, r1 = +-sv (t0 - a t1), a = c1/c0      (kind 0)       one complex multiply, four additions
+//   r0 = a t0 + t1, r1 = +-sv (a t0 - t1), a = c0/c1      (kind 1)       (12 FP64 operations per pair instead of 21).
+// The CZ signs are sign-bit XORs: the parity of the thread's fixed index bits is taken once per stage and combined with
+// a host-made 8-bit table (qtab / vtab: parity contributed by the register-axis bits of slot `lo`).
 struct Stage {
-  double2 m00, m01, m10, m11;
+  double2 m00, m01, m10, m11;    // the unfactored 2x2 (kind 2; also what a batch of one hands to k_fused)
+  double2 a;                     // kinds 0 / 1: the one multiplier left after taking f out
   unsigned long long mq, mv;
-  int axis;
-  int pad;
+  int axis;                      // batch axis index
+  unsigned char kind;            // 0 / 1 / 2, see above
+  unsigned char neg;             // kinds 0/1: s1 = -s0
+  unsigned char qtab, vtab;      // set when the pass is launched (depend on the register assignment of the axes)
 };
 struct Batch {
   int nstages;
   int naxes;
   unsigned char axbit[8];
+  double nscale[MAX_STAGES];     // prod_{i <= k} |f_i|^2: stored norm -> norm of the unfactored state after stage k
   Stage st[MAX_STAGES];
 };
+
+__device__ __forceinline__ double flip_sign(const double x, const unsigned int s31) {   // s31 = 0 or 0x80000000
+  return __hiloint2double(__double2hiint(x) ^ (int)s31, __double2loint(x));
+}
+
+// Apply stage `st` on register axis AX of the 2^NB amplitudes a thread holds; gpar_q / gpar_v = parity of the thread's
+// fixed physical index bits in st.mq / st.mv.  Adds the norm^2 of the 2^NB results to nrm0 / nrm1 (two chains).
+template <int NB, int AX>
+__device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage& st, const unsigned int gpar_q,
+                                              const unsigned int gpar_v, double& nrm0, double& nrm1) {
+  // bit lo of tq / tv = 1 iff the amplitude pair of slot lo takes the sign
+  const unsigned int tq = (gpar_q & 1u) ? ~(unsigned int)st.qtab : (unsigned int)st.qtab;
+  const unsigned int tv = ((gpar_v ^ st.neg) & 1u) ? ~(unsigned int)st.vtab : (unsigned int)st.vtab;
+  const double2 a = st.a;
+  if (st.kind == 0) {
+#pragma unroll
+    for (int lo = 0; lo < (1 << NB); ++lo) {
+      if ((lo >> AX) & 1) continue;
+      const int hi = lo | (1 << AX);
+      const unsigned int sq = (tq << (31 - lo)) & 0x80000000u, sv = (tv << (31 - lo)) & 0x80000000u;
+      double2 w = cmul(a, v[hi]);
+      w.x = flip_sign(w.x, sq);
+      w.y = flip_sign(w.y, sq);
+      const double2 r0 = make_double2(v[lo].x + w.x, v[lo].y + w.y);
+      const double2 r1 = make_double2(flip_sign(v[lo].x - w.x, sv), flip_sign(v[lo].y - w.y, sv));
+      nrm0 = fma(r0.x, r0.x, nrm0); nrm1 = fma(r0.y, r0.y, nrm1);
+      nrm0 = fma(r1.x, r1.x, nrm0); nrm1 = fma(r1.y, r1.y, nrm1);
+      v[lo] = r0;
+      v[hi] = r1;
+    }
+  } else if (st.kind == 1) {
+#pragma unroll
+    for (int lo = 0; lo < (1 << NB); ++lo) {
+      if ((lo >> AX) & 1) continue;
+      const int hi = lo | (1 << AX);
+      const unsigned int sq = (tq << (31 - lo)) & 0x80000000u, sv = (tv << (31 - lo)) & 0x80000000u;
+      const double2 u = cmul(a, v[lo]);
+      const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
+      const double2 r0 = make_double2(u.x + t1.x, u.y + t1.y);
+      const double2 r1 = make_double2(flip_sign(u.x - t1.x, sv), flip_sign(u.y - t1.y, sv));
+      nrm0 = fma(r0.x, r0.x, nrm0); nrm1 = fma(r0.y, r0.y, nrm1);
+      nrm0 = fma(r1.x, r1.x, nrm0); nrm1 = fma(r1.y, r1.y, nrm1);
+      v[lo] = r0;
+      v[hi] = r1;
+    }
+  } else {
+    const double2 m00 = st.m00, m01 = st.m01, m10 = st.m10, m11 = st.m11;
+#pragma unroll
+    for (int lo = 0; lo < (1 << NB); ++lo) {
+      if ((lo >> AX) & 1) continue;
+      const int hi = lo | (1 << AX);
+      const unsigned int sq = (tq << (31 - lo)) & 0x80000000u, sv = (tv << (31 - lo)) & 0x80000000u;
+      const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
+      const double2 r0 = cmad2(m00, v[lo], m01, t1);
+      double2 r1 = cmad2(m10, v[lo], m11, t1);
+      r1.x = flip_sign(r1.x, sv);
+      r1.y = flip_sign(r1.y, sv);
+      nrm0 = fma(r0.x, r0.x, nrm0); nrm1 = fma(r0.y, r0.y, nrm1);
+      nrm0 = fma(r1.x, r1.x, nrm0); nrm1 = fma(r1.y, r1.y, nrm1);
+      v[lo] = r0;
+      v[hi] = r1;
+    }
+  }
+}
+
+// Batch on at most three physical bits: a thread owns the 2^A amplitudes of one group in registers and applies the
+// stages in order (64 registers, 4 CTAs per SM; the per-thread stage accumulators live in shared memory).
+// CTAs take chunks of 2^glog consecutive 256-group blocks (glog = 0: plain grid stride).
 template <int A>
-__global__ void __launch_bounds__(TPB, (A <= 3) ? 4 : 2) k_fused_batch(double2* __restrict__ psi, const __grid_constant__ Holes hs,
-                                                     const __grid_constant__ Batch bt, const uint64_t ngroups,
-                                                     double* __restrict__ partials, Ctrl* ctrl, Res* res,
-                                                     const unsigned long long seq, const int fin_mode) {
+__global__ void __launch_bounds__(TPB, 4) k_fused_batch(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+                                                       const __grid_constant__ Batch bt, const uint64_t ngroups,
+                                                       const int glog, double* __restrict__ partials, Ctrl* ctrl,
+                                                       Res* res, const unsigned long long seq, const int fin_mode) {
   constexpr int D = 1 << A;
   const double g = ctrl->g;
   // offset of register slot b = OR of the axis bits set in b; only the A single-bit offsets are kept live
@@ -409,12 +496,14 @@ __global__ void __launch_bounds__(TPB, (A <= 3) ? 4 : 2) k_fused_batch(double2* 
       if ((b >> a) & 1) o |= ax[a];
     return o;
   };
-  // per-thread stage accumulators live in shared memory (one column per thread, no conflicts): 16 registers less,
-  // which is what gets the kernel to 4 CTAs per SM
   __shared__ double sacc[MAX_STAGES][TPB];
 #pragma unroll
   for (int k = 0; k < MAX_STAGES; ++k) sacc[k][threadIdx.x] = 0.0;
-  for (uint64_t j = (uint64_t)blockIdx.x * TPB + threadIdx.x; j < ngroups; j += (uint64_t)gridDim.x * TPB) {
+  const uint64_t nblk = (ngroups + TPB - 1) / TPB;
+  for (uint64_t blk0 = (uint64_t)blockIdx.x << glog; blk0 < nblk; blk0 += (uint64_t)gridDim.x << glog)
+  for (uint64_t blk = blk0; blk < blk0 + (1ull << glog); ++blk) {
+    const uint64_t j = blk * TPB + threadIdx.x;
+    if (j >= ngroups) break;
     const uint64_t base = expand(j, hs);
     double2 v[D];
 #pragma unroll
@@ -422,34 +511,15 @@ __global__ void __launch_bounds__(TPB, (A <= 3) ? 4 : 2) k_fused_batch(double2* 
       const double2 a = ld_amp(psi + base + off_of(b));
       v[b] = make_double2(g * a.x, g * a.y);       // the pending normalisation, once per pass
     }
-#pragma unroll
-    for (int s = 0; s < MAX_STAGES; ++s) {
-      if (s < bt.nstages) {
-        const Stage& st = bt.st[s];
-        double nrm = 0.0;
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-          if (st.axis == a) {
-#pragma unroll
-            for (int lo = 0; lo < D; ++lo) {
-              if ((lo >> a) & 1) continue;
-              const int hi = lo | (1 << a);
-              const uint64_t idx = base + off_of(lo);
-              // queued CZ signs: conditional negation, no multiplies
-              const bool nq = __popcll(idx & st.mq) & 1;
-              const bool nv = __popcll(idx & st.mv) & 1;
-              const double2 t1 = nq ? make_double2(-v[hi].x, -v[hi].y) : v[hi];
-              const double2 r0 = cmad2(st.m00, v[lo], st.m01, t1);
-              double2 r1 = cmad2(st.m10, v[lo], st.m11, t1);
-              if (nv) { r1.x = -r1.x; r1.y = -r1.y; }
-              nrm += cnorm2(r0) + cnorm2(r1);
-              v[lo] = r0;
-              v[hi] = r1;
-            }
-          }
-        }
-        sacc[s][threadIdx.x] += nrm;
-      }
+    for (int s = 0; s < bt.nstages; ++s) {
+      const Stage& st = bt.st[s];
+      const unsigned int pq = __popcll(base & st.mq), pv = __popcll(base & st.mv);
+      double n0 = 0.0, n1 = 0.0;
+      const int la = st.axis;
+      if (la == 0) stage_on_axis<A, 0>(v, st, pq, pv, n0, n1);
+      if (A > 1 && la == 1) stage_on_axis<A, (A > 1 ? 1 : 0)>(v, st, pq, pv, n0, n1);
+      if (A > 2 && la == 2) stage_on_axis<A, (A > 2 ? 2 : 0)>(v, st, pq, pv, n0, n1);
+      sacc[s][threadIdx.x] += n0 + n1;
     }
 #pragma unroll
     for (int b = 0; b < D; ++b) st_amp(psi + base + off_of(b), v[b]);
@@ -457,7 +527,284 @@ __global__ void __launch_bounds__(TPB, (A <= 3) ? 4 : 2) k_fused_batch(double2* 
   double acc[MAX_STAGES];
 #pragma unroll
   for (int k = 0; k < MAX_STAGES; ++k) acc[k] = sacc[k][threadIdx.x];
-  grid_finish<MAX_STAGES>(acc, partials, ctrl, res, seq, fin_mode, (double)bt.nstages, g);
+  grid_finish<MAX_STAGES>(acc, partials, ctrl, res, seq, fin_mode, (double)bt.nstages, g, bt.nscale);
+}
+
+// ---------------------------------------------------------------------------
+// Batched lazy projections on MORE than three physical bits (4 <= A <= 6): the register file holds 2^3 amplitudes per
+// thread at 4 CTAs per SM (k_fused_batch above), so a batch whose stages touch up to 6 distinct bits is executed in
+// PHASES.  Every WARP owns a tile of 2^8 amplitudes = 2^A axis combinations x 2^(8-A) consecutive dense indices; the 8
+// warps of a CTA take 8 consecutive warp tiles, so that the CTA as a whole still reads 2^(11-A) consecutive amplitudes
+// (>= 512 B) per axis combination.  In a phase every thread keeps the 2^3 combinations of three of the axes in
+// registers (the other A - 3 axis values and the dense index are fixed per lane) and applies the consecutive stages
+// that act on those three axes; between phases the warp transposes its tile through its private 4 KB of shared
+// memory to the register assignment of the next phase.  Only __syncwarp is needed: the warps stay independent, so the
+// FP64 work of one warp overlaps the loads and stores of the others exactly as in the single-phase kernel.
+// (Measured first: the same scheme with ONE tile of 2^11 amplitudes per CTA and __syncthreads between phases ran 8 stages
+// on 5 axes in 1.37 ms at 27 qubits against 0.81 ms for 8 stages on 3 axes in k_fused_batch: the CTA-wide barriers
+// serialise the memory and FP64 phases.)  HBM traffic stays one read and one write of the register per pass whatever
+// the number of stages and phases; the host plans the phases greedily (longest run of stages on <= 3 distinct axes; at
+// most MAX_PHASES per pass).  Tiles are handed to CTAs in chunks of 2^glog consecutive CTA tiles.
+// ---------------------------------------------------------------------------
+constexpr int TILE_LOG2 = 11;      // amplitudes per CTA iteration
+constexpr int WTILE_LOG2 = 8;      // amplitudes per warp tile
+constexpr int MAX_TILE_AXES = 6;
+constexpr int MAX_PHASES = 4;
+struct Phase {
+  unsigned char ax[3];    // batch-axis indices held in registers during this phase
+  unsigned char oth[3];   // the remaining naxes - 3 batch axes (their values are fixed per thread)
+  unsigned char s_begin, s_end;
+};
+struct TileBatch {
+  int nstages, naxes, nphases, pad;
+  unsigned char axbit[8];          // physical bit of every batch axis
+  unsigned char lax[MAX_STAGES];   // register slot (0..2) of the axis of every stage inside its phase
+  Phase ph[MAX_PHASES];
+  double nscale[MAX_STAGES];
+  Stage st[MAX_STAGES];
+};
+__global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+                                                      const __grid_constant__ TileBatch bt, const uint64_t ntiles,
+                                                      const int glog, double* __restrict__ partials, Ctrl* ctrl,
+                                                      Res* res, const unsigned long long seq, const int fin_mode) {
+  extern __shared__ double2 tile_all[];             // 8 warps x 2^WTILE_LOG2 amplitudes (dynamic: 32 KB)
+  __shared__ double sacc[MAX_STAGES][TPB];
+  const int A = bt.naxes, F = WTILE_LOG2 - A;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double2* tile = tile_all + ((size_t)warp << WTILE_LOG2);
+  const unsigned int f = lane & ((1u << F) - 1u);
+  const int r = lane >> F;
+  const double g = ctrl->g;
+#pragma unroll
+  for (int k = 0; k < MAX_STAGES; ++k) sacc[k][tid] = 0.0;
+  const uint64_t nchunks = (ntiles + (1ull << glog) - 1ull) >> glog;
+  for (uint64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (uint64_t it = 0; it < (1ull << glog); ++it) {
+      const uint64_t t = (chunk << glog) + it;
+      if (t >= ntiles) break;
+      const uint64_t wt = t * (TPB / 32) + warp;    // this warp's tile
+      const uint64_t base = expand((wt << F) | f, hs);
+      double2 v[8];
+      for (int p = 0; p < bt.nphases; ++p) {
+        const Phase& ph = bt.ph[p];
+        uint64_t gthread = base;                    // physical index of this thread's group (register axes = 0)
+        unsigned int sthread = 0;                   // same, as axis-combination index of the warp's shared-memory tile
+        for (int i = 0; i < A - 3; ++i)
+          if ((r >> i) & 1) {
+            gthread |= 1ull << bt.axbit[ph.oth[i]];
+            sthread |= 1u << ph.oth[i];
+          }
+        uint64_t gax[3];
+        unsigned int sax[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          gax[i] = 1ull << bt.axbit[ph.ax[i]];
+          sax[i] = 1u << ph.ax[i];
+        }
+        auto goff = [&](int b) {
+          uint64_t o = 0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if ((b >> i) & 1) o |= gax[i];
+          return o;
+        };
+        auto soff = [&](int b) {
+          unsigned int o = sthread;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if ((b >> i) & 1) o |= sax[i];
+          return (o << F) | f;
+        };
+        if (p == 0) {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            const double2 a = ld_amp(psi + gthread + goff(b));
+            v[b] = make_double2(g * a.x, g * a.y);  // the pending normalisation, once per pass
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) v[b] = tile[soff(b)];
+        }
+        for (int s = ph.s_begin; s < ph.s_end; ++s) {
+          const Stage& st = bt.st[s];
+          const unsigned int pq = __popcll(gthread & st.mq), pv = __popcll(gthread & st.mv);
+          double n0 = 0.0, n1 = 0.0;
+          const int la = bt.lax[s];
+          if (la == 0) stage_on_axis<3, 0>(v, st, pq, pv, n0, n1);
+          else if (la == 1) stage_on_axis<3, 1>(v, st, pq, pv, n0, n1);
+          else stage_on_axis<3, 2>(v, st, pq, pv, n0, n1);
+          sacc[s][tid] += n0 + n1;
+        }
+        if (p + 1 < bt.nphases) {
+          __syncwarp();                             // every lane has read its slots of the previous transpose
+#pragma unroll
+          for (int b = 0; b < 8; ++b) tile[soff(b)] = v[b];
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) st_amp(psi + gthread + goff(b), v[b]);
+        }
+      }
+    }
+  }
+  double acc[MAX_STAGES];
+#pragma unroll
+  for (int k = 0; k < MAX_STAGES; ++k) acc[k] = sacc[k][tid];
+  grid_finish<MAX_STAGES>(acc, partials, ctrl, res, seq, fin_mode, (double)bt.nstages, g, bt.nscale);
+}
+
+// ---------------------------------------------------------------------------
+// The same batched pass with the CTA tile staged through shared memory by the bulk-copy engine (TMA, cp.async.bulk):
+// the bytes in flight live in shared memory instead of registers, loads of tile i+1 and stores of tile i-1 overlap the
+// FP64 work on tile i, and no thread computes a global address.
+//   tile   = 2^H runs of 2^L physically contiguous amplitudes (L + H = 11): the low L physical bits entirely (batch axes
+//            below bit L are simply part of the run) x the 2^H combinations of the batch axes at / above bit L.  One bulk
+//            copy per run (>= 512 B), 2^H <= 64 copies per tile, issued by the lanes of warp 0 and tracked by an mbarrier
+//            (loads) / a bulk group (stores).  Three tile buffers: tile i+1 loads while tile i is computed and tile
+//            i-1 drains.
+//   phases = as in k_fused_tile, but IN PLACE in the tile buffer: a thread reads the 2^3 amplitudes spanned by the three
+//            register bits of the phase (any of the 11 tile-index bits), applies the stages of the phase, writes them back
+//            to the same slots; one __syncthreads between phases.
+// 96 KB of buffers + 16 KB of stage accumulators per CTA, 2 CTAs per SM.  Used when no dead bit lies below bit L.
+// ---------------------------------------------------------------------------
+struct TmaBatch {
+  int nstages, nphases, L, H;
+  unsigned char hbit[8];           // physical bit of tile-index bit L + i
+  unsigned char lax[MAX_STAGES];   // register slot (0..2) of the axis of every stage inside its phase
+  unsigned char sb[MAX_PHASES][4]; // register bits of every phase as tile-index bits, ascending
+  unsigned char s_begin[MAX_PHASES], s_end[MAX_PHASES];
+  double nscale[MAX_STAGES];
+  Stage st[MAX_STAGES];
+};
+constexpr int TMA_BUFS = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TPB, 2) k_fused_tma(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+                                                     const __grid_constant__ TmaBatch bt, const uint64_t ntiles,
+                                                     double* __restrict__ partials, Ctrl* ctrl, Res* res,
+                                                     const unsigned long long seq, const int fin_mode) {
+  extern __shared__ __align__(128) double2 tbuf[];    // TMA_BUFS x 2^TILE_LOG2 amplitudes
+  __shared__ double sacc[MAX_STAGES][TPB];
+  __shared__ __align__(8) unsigned long long full[TMA_BUFS];
+  constexpr uint32_t TILE = 1u << TILE_LOG2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = bt.L, H = bt.H;
+  const uint32_t run_bytes = 16u << L;
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < TMA_BUFS; ++b) mbar_init(&full[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#pragma unroll
+  for (int k = 0; k < MAX_STAGES; ++k) sacc[k][tid] = 0.0;
+  __syncthreads();
+  const double g = ctrl->g;
+  // physical offset of run r of a tile (lanes of warp 0 own runs lane, lane + 32)
+  auto run_off = [&](int r) {
+    uint64_t o = 0;
+    for (int i = 0; i < H; ++i)
+      if ((r >> i) & 1) o |= 1ull << bt.hbit[i];
+    return o;
+  };
+  auto issue_load = [&](uint64_t t, int b) {           // whole warp 0
+    const uint64_t base = expand(t << L, hs);
+    if (lane == 0) mbar_arrive_expect_tx(&full[b], TILE * 16u);
+    __syncwarp();
+    for (int r = lane; r < (1 << H); r += 32)
+      bulk_load(tbuf + (size_t)b * TILE + ((size_t)r << L), psi + base + run_off(r), run_bytes, &full[b]);
+  };
+  if (warp == 0 && blockIdx.x < ntiles) issue_load(blockIdx.x, 0);
+  uint32_t it = 0;
+  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int b = it % TMA_BUFS;
+    const uint32_t parity = (it / TMA_BUFS) & 1u;
+    const uint64_t tn = t + gridDim.x;
+    if (warp == 0 && tn < ntiles) {
+      bulk_wait_read<1>();                  // the stores that last read the next buffer (two tiles ago) have drained
+      issue_load(tn, (it + 1) % TMA_BUFS);
+    }
+    double2* tb = tbuf + (size_t)b * TILE;
+    const uint64_t base = expand(t << L, hs);
+    mbar_wait(&full[b], parity);
+    for (int p = 0; p < bt.nphases; ++p) {
+      // this thread's tile index with the three register bits (ascending) cleared
+      unsigned int sidx = tid;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const unsigned int lo = sidx & ((1u << bt.sb[p][k]) - 1u);
+        sidx = ((sidx - lo) << 1) | lo;
+      }
+      uint64_t gthread = base | (uint64_t)(sidx & ((1u << L) - 1u));
+      for (int i = 0; i < H; ++i)
+        if ((sidx >> (L + i)) & 1u) gthread |= 1ull << bt.hbit[i];
+      const unsigned int s0 = 1u << bt.sb[p][0], s1 = 1u << bt.sb[p][1], s2 = 1u << bt.sb[p][2];
+      auto soff = [&](int bb) { return sidx | ((bb & 1) ? s0 : 0u) | ((bb & 2) ? s1 : 0u) | ((bb & 4) ? s2 : 0u); };
+      double2 v[8];
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) v[bb] = tb[soff(bb)];
+      if (p == 0) {
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb) { v[bb].x *= g; v[bb].y *= g; }   // the pending normalisation, once per pass
+      }
+      for (int s = bt.s_begin[p]; s < bt.s_end[p]; ++s) {
+        const Stage& st = bt.st[s];
+        const unsigned int pq = __popcll(gthread & st.mq), pv = __popcll(gthread & st.mv);
+        double n0 = 0.0, n1 = 0.0;
+        const int la = bt.lax[s];
+        if (la == 0) stage_on_axis<3, 0>(v, st, pq, pv, n0, n1);
+        else if (la == 1) stage_on_axis<3, 1>(v, st, pq, pv, n0, n1);
+        else stage_on_axis<3, 2>(v, st, pq, pv, n0, n1);
+        sacc[s][tid] += n0 + n1;
+      }
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) tb[soff(bb)] = v[bb];
+      if (p + 1 < bt.nphases) __syncthreads();
+    }
+    fence_proxy_async();                    // generic-proxy writes of the tile -> visible to the bulk-copy engine
+    __syncthreads();
+    if (warp == 0) {
+      for (int r = lane; r < (1 << H); r += 32)
+        bulk_store(psi + base + run_off(r), tb + ((size_t)r << L), run_bytes);
+      bulk_commit();
+    }
+  }
+  if (warp == 0) bulk_wait_all<0>();
+  double acc[MAX_STAGES];
+#pragma unroll
+  for (int k = 0; k < MAX_STAGES; ++k) acc[k] = sacc[k][tid];
+  grid_finish<MAX_STAGES>(acc, partials, ctrl, res, seq, fin_mode, (double)bt.nstages, g, bt.nscale);
 }
 
 // ---------------------------------------------------------------------------

@@ -427,3 +427,47 @@ def test_large_state_roundtrip_properties():
     assert sv.nqubit == n
     assert abs(sv.norm2() - 1) < 1e-12
     assert abs(sv.fidelity(ref) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("tma", [0, 1])
+@pytest.mark.parametrize("axes,glog", [(1, 0), (2, 1), (3, 0), (3, 3), (4, 0), (4, 2), (5, 0), (5, 3), (6, 0), (6, 1)])
+@pytest.mark.parametrize("n", [12, 15, 17])
+def test_batched_passes_on_many_axes_against_oracle(n, axes, glog, tma):
+    """Non-strict batches of up to 8 fused (N, E.., M) stages on up to `axes` distinct physical bits: more than three
+    axes run the phased shared-memory tile kernel (k_fused_tile).  Random measured qubits (so the axis sets, the phase
+    plans and the low / high bit positions vary), CZs to neighbours of both the measured and the new qubit, non-|+>
+    preparations; compared with the oracle entry by entry (phase included)."""
+    from graphix_b200 import _lib
+
+    rng = np.random.default_rng(1000 * n + 10 * axes + glog)
+    psi = rand_state(rng, n)
+    dev = _sv(psi, n + 1, fusion=2, strict=False, batch=8)
+    dev.set_option(_lib.OPT_BATCH_AXES, axes)
+    dev.set_option(_lib.OPT_CHUNK_LOG2, glog)
+    dev.set_option(_lib.OPT_TMA, tma)     # 1: tiles staged by bulk copies (k_fused_tma); 0: register-staged kernels
+    orc = OracleStatevector(psi, max_qubits=n + 1)
+    npass0 = dev.stats()["fused"]["launches"]
+    for step in range(48):
+        m = int(rng.integers(n))
+        others = [int(x) for x in rng.choice([i for i in range(n) if i != m], size=3, replace=False)]
+        st = [mbqc.BasicStates.PLUS, mbqc.PlanarState(mbqc.Plane.XY, 0.3), mbqc.BasicStates.MINUS,
+              mbqc.PlanarState(mbqc.Plane.YZ, 0.7)][int(rng.integers(4))]
+        vec = rng.normal(size=3)
+        vec /= np.linalg.norm(vec)
+        pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
+        for s in (dev, orc):
+            s.add_nodes(1, st)
+            s.entangle((n, m))
+            s.entangle((m, others[0]))
+            if step % 2:
+                s.entangle((n, others[1]))
+            if step % 3 == 0:
+                s.entangle((m, others[2]))
+            s.project_qubit(pm, m)
+        if step % 16 == 15:
+            np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
+    np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
+    assert abs(dev.norm2() - 1) < 1e-12
+    passes = dev.stats()["fused"]["launches"] - npass0
+    if axes >= 5:
+        assert passes <= 16          # 48 stages: at least three per pass on average

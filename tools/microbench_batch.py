@@ -1,0 +1,90 @@
+"""Batched-projection pass timing as a function of register size, axis positions, axes per pass and chunking
+(run on the GPU box):  python tools/microbench_batch.py <n materialised qubits> [reps]
+
+Every case builds batches of fused (N, E, M) stages on chosen PHYSICAL bits through the public API and reports the
+CUDA-event time per pass of the `fused` kernel kind (k_fused / k_fused_batch / k_fused_tile)."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+from graphix_b200 import B200Statevector, _lib, mbqc  # noqa: E402
+
+
+def proj(vec, r):
+    x, y, z = vec
+    s = -1.0 if r else 1.0
+    return np.array([[0.5 + 0.5 * s * z, 0.5 * s * (x - 1j * y)], [0.5 * s * (x + 1j * y), 0.5 - 0.5 * s * z]])
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 27
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    sv = B200Statevector(nqubit=0, max_qubits=n, strict=False, batch=8)
+    sv.add_nodes(n, mbqc.BasicStates.PLUS)
+    sv.flush()
+    sv.sync()
+    sv.set_option(_lib.OPT_PROFILE, 1)
+    pm = proj(mbqc.Plane.XY.polar(0.3), 0)
+    rows = []
+    hi = n - 1
+
+    def run(label, axes, stages, batch_axes, glog, tma=int(os.environ.get("MB_TMA", "1"))):
+        sv.set_option(_lib.OPT_TMA, tma)
+        sv.set_option(_lib.OPT_BATCH_AXES, batch_axes)
+        sv.set_option(_lib.OPT_CHUNK_LOG2, glog)
+        sv.set_option(_lib.OPT_BATCH, min(8, stages))
+        for timed in (False, True):
+            sv.sync()
+            sv.reset_stats()
+            for _ in range(reps if timed else 1):
+                for s in range(stages):
+                    p = axes[s % len(axes)]
+                    q = sv.layout().index(p)
+                    sv.add_nodes(1, mbqc.BasicStates.PLUS)
+                    sv.entangle((sv.nqubit - 1, q))
+                    sv.project_qubit(pm, q)
+                sv.flush() if False else None
+            sv.sync()
+        st = sv.stats()["fused"]
+        ms = st["device_ms"] / max(st["launches"], 1)
+        gbs = st["algo_bytes"] / (st["device_ms"] * 1e-3) / 1e9 if st["device_ms"] else 0.0
+        rows.append({"n": n, "case": label, "axes": list(axes), "stages": stages, "batch_axes": batch_axes, "glog": glog,
+                     "launches": st["launches"], "ms_per_pass": ms, "algo_GBps": gbs})
+        print(f"n={n} {label:28s} axes={str(list(axes)):26s} stages={stages} A<={batch_axes} glog={glog}: "
+              f"{st['launches']:3d} passes {ms:9.4f} ms  {gbs:7.1f} GB/s", flush=True)
+
+    lowmid = (9, 10, 11)
+    mid = (n // 2 - 1, n // 2, n // 2 + 1)
+    top = (hi - 2, hi - 1, hi)
+    spread = (9, n // 2, hi)
+    # 1) one stage per pass (k_fused, two streams) vs position
+    for ax in ((10,), (n // 2,), (hi,)):
+        run("1 axis, 1 stage", ax, 1, 3, 0)
+    # 2) three axes, three stages (k_fused_batch<3>, eight streams): position and chunking
+    for name, ax in (("low", lowmid), ("mid", mid), ("top", top), ("spread", spread)):
+        for glog in (3,):
+            run(f"3 axes {name}", ax, 3, 3, glog)
+    # 3) k_fused_tile: 4 / 5 / 6 axes, 8 stages
+    five_top = (hi - 4, hi - 3, hi - 2, hi - 1, hi)
+    five_spread = (8, 12, n // 2, hi - 3, hi)
+    six = (8, 12, n // 2, hi - 5, hi - 2, hi)
+    for name, ax in (("4 axes spread", (9, n // 2, hi - 2, hi)), ("5 axes top", five_top), ("5 axes spread", five_spread),
+                     ("6 axes", six)):
+        run(name, ax, 8, len(ax), 3)
+    # the same 8 stages on 5 axes as 3-axis passes (what round 1 ran)
+    run("5 axes spread via A<=3", five_spread, 8, 3, 3)
+    run("5 axes incl. low bits", (1, 4, n // 2, hi - 3, hi), 8, 5, 3)
+    run("3 axes, 8 stages", spread, 8, 3, 3)
+    print("norm2", sv.norm2())
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/microbench_batch_{n}.json", "w") as f:
+        json.dump(rows, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
