@@ -220,6 +220,259 @@ def reference_arm(args) -> None:
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+class SeededOutcomes:
+    """Deterministic pseudo-random outcomes that never ask for a probability (flow patterns: every p = 1/2)."""
+
+    def __init__(self, seed: int) -> None:
+        self.seed = seed
+        self.rng = np.random.default_rng(seed)
+
+    def measure(self, qubit, f_expectation0, rng=None, *, stacklevel=1):  # noqa: ARG002
+        return int(self.rng.integers(2))
+
+
+def kernel_table(stats: dict, steps: int, peak: float) -> dict:
+    return {k: {"launches_per_step": v["launches"] / steps, "ms_per_launch": v["device_ms"] / v["launches"],
+                "GBps": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9,
+                "frac_of_measured_peak": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9 / peak}
+            for k, v in stats.items() if v["launches"] and v["device_ms"] > 0}
+
+
+def roofline_of(stats: dict, dev_ms: float, traffic=None) -> dict:
+    """Dominant kernel (by summed CUDA-event time inside the timed region) against the measured HBM copy rate."""
+    peak, peak_src = measured_peak()
+    kinds = {k: v for k, v in stats.items() if v["launches"] and v["device_ms"] > 0}
+    dom = max(kinds, key=lambda k: kinds[k]["device_ms"])
+    d = kinds[dom]
+    achieved = d["algo_bytes"] / (d["device_ms"] * 1e-3) / 1e9
+    total_ms = sum(v["device_ms"] for v in kinds.values())
+    total_bytes = sum(v["algo_bytes"] for v in kinds.values())
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / NOMINAL_HBM_GBS, "traffic": traffic,
+            "algo_bytes_per_launch": d["algo_bytes"] / d["launches"], "avg_launch_ms": d["device_ms"] / d["launches"],
+            "share_of_kernel_time": d["device_ms"] / total_ms,
+            "all_kernels_achieved": total_bytes / (total_ms * 1e-3) / 1e9,
+            "all_kernels_frac": total_bytes / (total_ms * 1e-3) / 1e9 / peak,
+            "kernel_time_share_of_step": total_ms / dev_ms}
+
+
+class Timer:
+    """Barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+
+    def __init__(self, world: int) -> None:
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.world = torch, dist, world
+
+    def barrier(self) -> None:
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, steps: int) -> float:
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = max(e0.elapsed_time(e1), 0.0)
+        self.wall_ms = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def timed_pattern(timer: Timer, backend, pattern, steps: int, warmup: int, run_kwargs=None, sharded: bool = False):
+    """W untimed + K timed complete runs of ``pattern`` on ``backend``; returns (device ms, engine stats)."""
+    from graphix_b200 import PatternSimulator, _lib
+
+    kw = run_kwargs or (lambda: {})
+
+    def one_step() -> None:
+        backend.state.reset()
+        backend.node_index.clear()
+        PatternSimulator(pattern, backend).run(**kw())
+
+    for _ in range(warmup):
+        one_step()
+    timer.barrier()
+    backend.state.reset_stats()
+    backend.state.set_option(_lib.OPT_PROFILE, 1)
+    if sharded:
+        backend.state.profile = True
+    ms = timer.run(one_step, steps)
+    stats = backend.state.stats()
+    backend.state.set_option(_lib.OPT_PROFILE, 0)
+    return ms, stats
+
+
+def exchange_record(st, steps: int) -> dict:
+    st.collect_profile()
+    rec = {"swaps_per_step": st.n_swaps / steps,
+           "nvlink_bytes_per_rank_per_step": st.exchanged_bytes / steps,
+           "device_ms_per_step": st.exchange_ms / steps,
+           "host_ms_per_step": st.exchange_host_ms / steps,
+           "host_wait_for_device_ms_per_step": st.sync_wait_ms / steps,
+           "GBps_per_direction": (st.exchanged_bytes / 1e9) / (st.exchange_ms * 1e-3) if st.exchange_ms else None,
+           "transport": getattr(st, "transport", "nccl send/recv")}
+    st.profile = False
+    return rec
+
+
+def free_device_memory() -> None:
+    import gc
+
+    import torch
+
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def make_gpu_backend(world: int, width: int, selector, *, fusion=2, nonstrict=True, batch=8, device=0, pattern=None,
+                     schedule=True):
+    from graphix_b200 import B200StatevectorBackend
+
+    if world > 1:
+        from graphix_b200.sharded import ShardedStatevectorBackend
+
+        return ShardedStatevectorBackend.with_capacity(width, branch_selector=selector, fusion=fusion,
+                                                       strict=not nonstrict, pattern=pattern if schedule else None)
+    lazy = fusion == 2 and nonstrict
+    return B200StatevectorBackend.with_capacity(width, branch_selector=selector, fusion=fusion, device=device,
+                                                strict=not lazy, batch=batch if lazy else 0)
+
+
+def sharded_parity(world: int) -> dict:
+    """Golden traces of the REFERENCE StatevectorBackend (tests/golden/patterns) replayed through the sharded backend
+    on the real NCCL ranks, strict and non-blocking: per-measurement p0 and final-state fidelity."""
+    from graphix_b200 import PatternSimulator, mbqc
+    from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern_dict, pattern_from_dict
+    from graphix_b200.sharded import ShardedStatevectorBackend
+
+    max_dp, min_fid, cases = 0.0, 1.0, 0
+    for name in ("qft13", "rand14x4", "nonflow22"):
+        d = load_pattern_dict(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
+        pattern = pattern_from_dict(d)
+        for trace in d["traces"][:2]:
+            if trace["input"]["kind"] != "plus":
+                continue
+            outcomes = {int(k): v for k, v in trace["outcomes"].items()}
+            ref = np.asarray(trace["final_state"], dtype=np.float64).view(np.complex128)
+            for strict, record in ((True, True), (False, False)):
+                fixed = mbqc.FixedBranchSelector(outcomes)
+                sel = mbqc.RecordingBranchSelector(fixed) if record else fixed
+                b = ShardedStatevectorBackend.with_capacity(pattern.max_space(), branch_selector=sel, strict=strict,
+                                                            pattern=pattern)
+                PatternSimulator(pattern, b).run()
+                if record:
+                    max_dp = max(max_dp, max(abs(sel.p0[int(k)] - v) for k, v in trace["p0"].items()))
+                flat = np.asarray(b.state.flatten())
+                min_fid = min(min_fid, float(abs(np.vdot(ref, flat)) ** 2))
+                cases += 1
+                del b
+    return {"max_dp0": max_dp, "min_fidelity": min_fid, "one_minus_min_fidelity": 1.0 - min_fid, "cases": cases,
+            "patterns": ["qft13", "rand14x4", "nonflow22"], "ranks": world,
+            "against": "reference StatevectorBackend traces committed under tests/golden/patterns"}
+
+
+def config3_record(args, timer: Timer, local_rank: int) -> dict:
+    """BASELINE config 3: QAOA MaxCut on K29 (examples/qaoa.py:19-29 generalised), 8352 commands, 29<->30 live qubits,
+    16 GiB register — the workload the '>= 70 % of HBM on a >= 30-live-qubit pattern' target is stated on."""
+    from graphix_b200 import mbqc
+    from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern
+
+    name = "config3_qaoa29"
+    pattern = load_pattern(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
+    width = pattern.max_space()
+    sel = mbqc.ConstBranchSelector(0)
+    out = {"workload": name, "commands_per_step": len(pattern), "live_qubits": f"{width - 1}<->{width}",
+           "state_bytes_max": 16 << width, "selector": "ConstBranchSelector(0)"}
+    # bench-default mode: lazy fusion, non-blocking batched projections, the whole pattern per step
+    b = make_gpu_backend(1, width, sel, device=local_rank, batch=args.batch)
+    ms, stats = timed_pattern(timer, b, pattern, 2, 1)
+    out["batched"] = {"value": len(pattern) * 2 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 2, "steps": 2, "warmup": 1,
+                      "roofline": roofline_of(stats, ms), "kernels": kernel_table(stats, 2, measured_peak()[0]),
+                      "projections_per_pass": sum(1 for c in pattern if c.kind.name == "M") * 2 / max(stats["fused"]["launches"], 1)}
+    del b
+    free_device_memory()
+    # strict lazy mode (reference error timing: every projection waits for its norm): a bounded prefix window
+    nwin = 2400
+    sub = mbqc.Pattern(pattern.input_nodes, list(pattern)[:nwin])
+    b = make_gpu_backend(1, width, sel, device=local_rank, nonstrict=False)
+    ms, stats = timed_pattern(timer, b, sub, 2, 1)
+    out["strict_lazy"] = {"value": nwin * 2 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 2, "steps": 2, "warmup": 1,
+                          "window": f"first {nwin} commands", "roofline": roofline_of(stats, ms),
+                          "kernels": kernel_table(stats, 2, measured_peak()[0])}
+    del b
+    free_device_memory()
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_cmds = 8
+        times = cpu_window(pattern, n_cmds, 1, 0)
+        if times:
+            out["cpu_baseline"] = {"value": n_cmds / times[0], "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{n_cmds} consecutive commands of {name} at {width - 1}<->{width} live "
+                                             f"qubits, {times[0]:.1f} s of CPU work"}
+    return out
+
+
+def config4_record(args, timer: Timer, world: int, local_rank: int) -> dict:
+    """BASELINE config 4: the QFT pattern of examples/qft_with_tn.py:22-56 at 33 + log2(N) live qubits on N GPUs
+    (128 GiB register per GPU at every point).  Timed on a bounded prefix window; then ONE complete run under
+    pseudo-random outcomes whose output is known: H on |+...+> gives |0...0>, whose QFT is |+...+>, so P(+) = 1 on every
+    output qubit whatever branch is taken, and the norm is 1."""
+    from graphix_b200 import PatternSimulator, mbqc
+    from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern
+
+    g = world.bit_length() - 1
+    name = f"config4_qft{32 + g}"
+    pattern = load_pattern(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
+    width = pattern.max_space()
+    nwin = args.config4_window
+    sub = mbqc.Pattern(pattern.input_nodes, list(pattern)[:nwin])
+    out = {"workload": name, "n_gpus": world, "live_qubits": f"{width - 1}<->{width}", "state_bytes_max": 16 << width,
+           "bytes_per_gpu": (16 << width) // world, "commands_full_pattern": len(pattern), "max_commands": nwin,
+           "selector": "ConstBranchSelector(0) (timed window); seeded pseudo-random outcomes (full run)"}
+    b = make_gpu_backend(world, width, mbqc.ConstBranchSelector(0), device=local_rank, batch=args.batch, pattern=sub)
+    ms, stats = timed_pattern(timer, b, sub, 2, 1, sharded=world > 1)
+    out.update({"value": nwin * 2 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 2, "steps": 2, "warmup": 1,
+                "roofline": roofline_of(stats, ms), "kernels": kernel_table(stats, 2, measured_peak()[0])})
+    if world > 1:
+        out["exchange"] = exchange_record(b.state, 2)
+    # complete run + known-answer check
+    if not args.no_parity:
+        sel = SeededOutcomes(11)
+        object.__setattr__(b, "branch_selector", sel)
+        if world > 1:
+            b.use_schedule(pattern)
+        b.state.reset()
+        b.node_index.clear()
+        timer.barrier()
+        t0 = time.perf_counter()
+        sim = PatternSimulator(pattern, b)
+        sim.run()
+        timer.barrier()
+        dt = time.perf_counter() - t0
+        plus = np.array([[0.5, 0.5], [0.5, 0.5]], dtype=np.complex128)
+        pmin = min(float(np.real(b.state.expectation_single(plus, q))) for q in range(b.state.nqubit))
+        norm2 = float(b.state.norm2())
+        ones = int(sum(sim.measure_method.results.values()))
+        out["parity_check"] = {"what": "complete pattern under seeded pseudo-random outcomes: QFT(H|+..+>) = |+..+>",
+                               "commands": len(pattern), "seconds": dt, "commands_per_s": len(pattern) / dt,
+                               "outcomes_equal_to_1": ones, "output_qubits": b.state.nqubit,
+                               "min_P_plus": pmin, "norm2": norm2,
+                               "ok": bool(abs(pmin - 1.0) < 1e-9 and abs(norm2 - 1.0) < 1e-9)}
+    del b
+    free_device_memory()
+    return out
+
+
 def gpu_arm(args) -> None:
     import torch
     import torch.distributed as dist
@@ -240,6 +493,7 @@ def gpu_arm(args) -> None:
     from graphix_b200 import B200StatevectorBackend, PatternSimulator, _lib, mbqc
     from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern
 
+    timer = Timer(world)
     name = workload_for(args.gpus, args.workload)
     pattern = load_pattern(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
     width = pattern.max_space()
@@ -252,143 +506,63 @@ def gpu_arm(args) -> None:
         selector = mbqc.RandomBranchSelector(pr_calc=True)
     else:
         selector = mbqc.ConstBranchSelector(0)
-    run_rng = (lambda: np.random.default_rng(0)) if args.selector == "random" else (lambda: None)
+    run_kwargs = (lambda: {"rng": np.random.default_rng(0)}) if args.selector == "random" else (lambda: {})
 
-    if world > 1:
-        from graphix_b200.sharded import ShardedStatevectorBackend
+    # ---- reference-derived parity of the sharded path on the real ranks (before anything is timed) -------------
+    shard_par = sharded_parity(world) if (world > 1 and not args.no_parity) else None
 
-        def make_backend():
-            # non-blocking projections: norms are all-reduced on the stream, the zero-norm check is deferred to finalize
-            return ShardedStatevectorBackend.with_capacity(width, branch_selector=selector, fusion=args.fusion,
-                                                           strict=not args.nonstrict,
-                                                           pattern=None if args.no_schedule else pattern)
-    else:
-        def make_backend():
-            # default: lazy fusion, non-blocking projections, up to --batch projections per pass
-            lazy = args.fusion == 2 and args.nonstrict
-            return B200StatevectorBackend.with_capacity(width, branch_selector=selector, fusion=args.fusion,
-                                                        device=local_rank, strict=not lazy,
-                                                        batch=args.batch if lazy else 0)
-
-    backend = make_backend()
-
-    def barrier() -> None:
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def one_step(profile: bool = False) -> None:
-        backend.state.reset()
-        backend.node_index.clear()
-        PatternSimulator(pattern, backend).run(rng=run_rng())
+    backend = make_gpu_backend(world, width, selector, fusion=args.fusion, nonstrict=args.nonstrict, batch=args.batch,
+                               device=local_rank, pattern=pattern, schedule=not args.no_schedule)
+    barrier = timer.barrier
 
     # ---- device-resident arm -------------------------------------------------
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
-    backend.state.reset_stats()
-    backend.state.set_option(_lib.OPT_PROFILE, 1)
-    if world > 1:
-        backend.state.profile = True
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof = None
     if args.cprofile and rank == 0:
         import cProfile
 
         prof = cProfile.Profile()
         prof.enable()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        one_step()
-    e1.record()
-    barrier()
+    dev_ms, stats = timed_pattern(timer, backend, pattern, args.steps, args.warmup, run_kwargs, sharded=world > 1)
     if prof is not None:
         import pstats
 
         prof.disable()
         pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(35)
     clocks = sampler.stop() if rank == 0 else {}
-    dev_ms = e0.elapsed_time(e1)
-    stats = backend.state.stats()
-    backend.state.set_option(_lib.OPT_PROFILE, 0)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
     value = ncmd * args.steps / (dev_ms * 1e-3)
-    exchange = None
-    if world > 1:
-        st = backend.state
-        st.collect_profile()
-        exchange = {"swaps_per_step": st.n_swaps / args.steps,
-                    "nvlink_bytes_per_rank_per_step": st.exchanged_bytes / args.steps,
-                    "device_ms_per_step": st.exchange_ms / args.steps,
-                    "host_ms_per_step": st.exchange_host_ms / args.steps,
-                    "host_wait_for_device_ms_per_step": st.sync_wait_ms / args.steps,
-                    "GBps_per_direction": (st.exchanged_bytes / 1e9) / (st.exchange_ms * 1e-3) if st.exchange_ms else None}
-        st.profile = False
+    exchange = exchange_record(backend.state, args.steps) if world > 1 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    # ---- secondary: the same pattern in the two stricter modes, same timing rules ----------
+    # ---- secondary: the same pattern in the stricter modes and under graphix's default selector, same timing rules --
     #   per_command : fusion = 1 — one kernel per command (runs of E fused), the north_star's per-command design
-    #   strict_lazy : fusion = 2, strict — lazy N/E->M fusion, every projection waits for its norm (reference
-    #                 error timing); `value` itself is fusion = 2, non-strict, batched
-    per_command = None
-    strict_lazy = None
-    if world == 1 and args.fusion == 2 and args.nonstrict and not args.no_per_command:
-        b2 = B200StatevectorBackend.with_capacity(width, branch_selector=selector, fusion=2, device=local_rank)
-        for _ in range(2):
-            b2.state.reset(); b2.node_index.clear(); PatternSimulator(pattern, b2).run()
-        b2.state.reset_stats()
-        b2.state.set_option(_lib.OPT_PROFILE, 1)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            b2.state.reset(); b2.node_index.clear(); PatternSimulator(pattern, b2).run()
-        e1.record()
-        barrier()
-        ms2 = e0.elapsed_time(e1)
-        st2 = {k: v for k, v in b2.state.stats().items() if v["launches"] and v["device_ms"] > 0}
-        peak2, _ = measured_peak()
-        strict_lazy = {"fusion": 2, "strict": True, "value": ncmd * args.steps / (ms2 * 1e-3), "unit": UNIT,
-                       "ms_per_step": ms2 / args.steps,
-                       "kernels": {k: {"launches_per_step": v["launches"] / args.steps,
-                                       "ms_per_launch": v["device_ms"] / v["launches"],
-                                       "frac_of_measured_peak": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9 / peak2}
-                                   for k, v in st2.items()}}
-        del b2
-    if world == 1 and args.fusion == 2 and not args.no_per_command:
-        b1 = B200StatevectorBackend.with_capacity(width, branch_selector=selector, fusion=1, device=local_rank)
-
-        def step1() -> None:
-            b1.state.reset()
-            b1.node_index.clear()
-            PatternSimulator(pattern, b1).run()
-
-        for _ in range(max(1, args.warmup - 1)):
-            step1()
-        b1.state.reset_stats()
-        b1.state.set_option(_lib.OPT_PROFILE, 1)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            step1()
-        e1.record()
-        barrier()
-        ms1 = e0.elapsed_time(e1)
-        st1 = {k: v for k, v in b1.state.stats().items() if v["launches"]}
-        peak1, _ = measured_peak()
-        per_command = {
-            "fusion": 1, "value": ncmd * args.steps / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1 / args.steps,
-            "kernels": {k: {"launches_per_step": v["launches"] / args.steps, "ms_per_launch": v["device_ms"] / v["launches"],
-                            "GBps": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9,
-                            "frac_of_measured_peak": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9 / peak1}
-                        for k, v in st1.items() if v["device_ms"] > 0},
-        }
-        del b1
+    #   strict_lazy : fusion = 2, strict — the library default: lazy N/E->M fusion, every projection waits for its
+    #                 norm (reference error timing); `value` itself is fusion = 2, non-strict, batched
+    #   random_selector : RandomBranchSelector(pr_calc=True), graphix's default — a probability query per measurement
+    per_command = strict_lazy = random_sel = None
+    peak = measured_peak()[0]
+    if world == 1 and args.fusion == 2 and args.nonstrict and not args.no_per_command and args.selector != "random":
+        for label, kw, sel2, rk in (("strict_lazy", {"nonstrict": False}, selector, lambda: {}),
+                                    ("random_selector", {"nonstrict": False}, mbqc.RandomBranchSelector(pr_calc=True),
+                                     lambda: {"rng": np.random.default_rng(0)}),
+                                    ("per_command", {"fusion": 1}, selector, lambda: {})):
+            b2 = make_gpu_backend(1, width, sel2, device=local_rank, **kw)
+            nst = max(2, args.steps - 2) if label != "strict_lazy" else args.steps
+            ms2, st2 = timed_pattern(timer, b2, pattern, nst, 2, rk)
+            rec = {"fusion": kw.get("fusion", 2), "strict": True, "value": ncmd * nst / (ms2 * 1e-3), "unit": UNIT,
+                   "ms_per_step": ms2 / nst, "steps": nst, "warmup": 2, "kernels": kernel_table(st2, nst, peak)}
+            if label == "strict_lazy":
+                rec["note"] = "library default (B200StatevectorBackend()): zero-norm RuntimeError raised by measure() itself"
+                strict_lazy = rec
+            elif label == "random_selector":
+                rec["selector"] = "RandomBranchSelector(pr_calc=True), rng=default_rng(0) (graphix's default selector)"
+                random_sel = rec
+            else:
+                per_command = rec
+            del b2
+            free_device_memory()
 
     # ---- end-to-end arm: host input vector in, host final state out ------------
     e2e = None
@@ -402,19 +576,12 @@ def gpu_arm(args) -> None:
         def e2e_step() -> None:
             backend.state.reset()
             backend.node_index.clear()
-            PatternSimulator(pattern, backend).run(input_state=np_in)   # H2D of the input state inside
-            backend.state.flatten(out=np_out)                             # D2H of the result inside
+            PatternSimulator(pattern, backend).run(input_state=np_in, **run_kwargs())   # H2D of the input state inside
+            backend.state.flatten(out=np_out)                                            # D2H of the result inside
 
         e2e_step()
-        barrier()
-        e0.record()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        e1.record()
-        barrier()
-        wall = time.perf_counter() - t0
-        e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+        e2e_dev = timer.run(e2e_step, args.steps)
+        e2e_ms = max(e2e_dev, timer.wall_ms)
         e2e = {"value": ncmd * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": 16 << n_in, "d2h_bytes_per_step": 16 << n_out,
                "ms_per_step": e2e_ms / args.steps}
@@ -437,20 +604,42 @@ def gpu_arm(args) -> None:
         host_out = torch.empty(1 << eng.nqubit, dtype=torch.complex128).pin_memory()
         np_out = host_out.numpy()
         e2e_step_sharded()
-        barrier()
-        e0.record()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step_sharded()
-        e1.record()
-        barrier()
-        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        e2e_dev = timer.run(e2e_step_sharded, args.steps)
+        t = torch.tensor([max(e2e_dev, timer.wall_ms)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
         e2e = {"value": ncmd * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": world * (16 << eng.nqubit), "ms_per_step": e2e_ms / args.steps,
                "note": "inputs are |+> product states (no upload); every rank reads its shard of the final state back"}
+
+    # ---- the GPU arm on exactly the command window the CPU baseline is timed on ------------------------------
+    same_window = None
+    cpu_n = None
+    if world == 1 and not args.no_cpu and width <= 31 and args.selector != "random":
+        cpu_n = args.cpu_window or (max(6, min(240, int(round(60 * 2.0 ** (27 - width))))) if width >= 22 else 600)
+        same_window = gpu_window(backend, pattern, cpu_n, timer)
+    del backend
+    free_device_memory()
+
+    # ---- BASELINE configs 3, 4 and 5 as sub-records of the same line (the driver only runs the default command) ---
+    extras = {}
+    default_run = args.workload is None and not args.max_commands and args.fusion == 2 and args.nonstrict and \
+        args.selector != "random" and not args.no_extra
+    if default_run:
+        if world == 1:
+            for key, fn in (("config3", lambda: config3_record(args, timer, local_rank)),
+                            ("config4", lambda: config4_record(args, timer, world, local_rank)),
+                            ("config5", lambda: dm_record(args, "config5_rand12x3", 3, 1))):
+                try:
+                    extras[key] = fn()
+                except Exception as exc:  # noqa: BLE001 - a sub-record must never take the headline line down
+                    extras[key] = {"error": f"{type(exc).__name__}: {exc}"}
+                free_device_memory()
+        else:
+            try:
+                extras["config4"] = config4_record(args, timer, world, local_rank)
+            except Exception as exc:  # noqa: BLE001
+                extras["config4"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
         if world > 1:
@@ -458,58 +647,99 @@ def gpu_arm(args) -> None:
         return
 
     # ---- roofline of the dominant kernel ---------------------------------------
-    peak, peak_src = measured_peak()
     kinds = {k: v for k, v in stats.items() if v["launches"]}
-    dom = max(kinds, key=lambda k: kinds[k]["device_ms"])
-    d = kinds[dom]
-    achieved = d["algo_bytes"] / (d["device_ms"] * 1e-3) / 1e9
-    total_kernel_ms = sum(v["device_ms"] for v in kinds.values())
-    total_bytes = sum(v["algo_bytes"] for v in kinds.values())
-    roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / NOMINAL_HBM_GBS,
-        "traffic": ncu_traffic(dom, name, bool(args.nonstrict and args.batch)) if world == 1 else None,
-        "algo_bytes_per_launch": d["algo_bytes"] / d["launches"], "avg_launch_ms": d["device_ms"] / d["launches"],
-        "share_of_kernel_time": d["device_ms"] / total_kernel_ms,
-        "all_kernels_achieved": total_bytes / (total_kernel_ms * 1e-3) / 1e9,
-        "all_kernels_frac": total_bytes / (total_kernel_ms * 1e-3) / 1e9 / peak,
-        "kernel_time_share_of_step": total_kernel_ms / dev_ms,
-    }
-    per_kind = {k: {"launches_per_step": v["launches"] / args.steps, "ms_per_launch": v["device_ms"] / v["launches"],
-                    "GBps": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9 if v["device_ms"] else None}
-                for k, v in kinds.items()}
+    roofline = roofline_of(stats, dev_ms)
+    roofline["traffic"] = ncu_traffic(roofline["kernel"], name, bool(args.nonstrict and args.batch)) if world == 1 else None
 
     # ---- CPU baseline: the oracle port on this box's cores, bounded window --------
     cpu_baseline = None
-    if world == 1 and not args.no_cpu and width <= 31:
+    if cpu_n:
         cores = os.cpu_count() or 1
-        n_cmds = args.cpu_window or (max(6, min(240, int(round(60 * 2.0 ** (27 - width))))) if width >= 22 else 600)
-        times = cpu_window(pattern, n_cmds, 1, 0)
+        times = cpu_window(pattern, cpu_n, 1, 0)
         if times:
-            cpu_baseline = {"value": n_cmds / times[0], "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"{n_cmds} consecutive commands of {name} at {width - 1}<->{width} live qubits, "
-                                      f"{times[0]:.1f} s of CPU work"}
+            cpu_baseline = {"value": cpu_n / times[0], "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{cpu_n} consecutive commands of {name} at {width - 1}<->{width} live qubits, "
+                                      f"{times[0]:.1f} s of CPU work",
+                            "gpu_same_window": same_window}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "c128", "data": "synthetic",
         "config": {"workload": name, "commands_per_step": ncmd, "live_qubits": f"{width - 1}<->{width}",
-                   "state_bytes_max": 16 << (width if world == 1 else width),
+                   "state_bytes_max": 16 << width,
                    "selector": "ConstBranchSelector(0)" if args.selector != "random" else "RandomBranchSelector(pr_calc=True), rng=default_rng(0)",
                    "fusion": args.fusion, "max_commands": args.max_commands or None,
                    "strict_norm_check": not args.nonstrict, "batch": args.batch if args.nonstrict else 0,
+                   "mode": "lazy N/E->M fusion, non-blocking batched projections (opt-in: strict=False, batch=8); the "
+                           "library default (strict) is reported as `strict_lazy`" if args.nonstrict and args.fusion == 2 else "as flagged",
                    "parallelism": f"shard{world}" if world > 1 else "single",
                    "l2": "state >> 126 MB L2: inputs larger than L2, no flush needed"},
         "e2e": e2e, "gpu_launches": int(sum(v["launches"] for v in kinds.values())),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": per_kind,
-        "per_command": per_command, "strict_lazy": strict_lazy,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "kernels": kernel_table(stats, args.steps, peak),
+        "projections_per_pass": (sum(1 for c in pattern if c.kind.name == "M") * args.steps / stats["fused"]["launches"])
+        if stats.get("fused", {}).get("launches") else None,
+        "per_command": per_command, "strict_lazy": strict_lazy, "random_selector": random_sel,
     }
     if world > 1:
         line["exchange"] = exchange
+        line["sharded_parity"] = shard_par
+    line.update(extras)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def gpu_window(backend, pattern, n_cmds: int, timer: "Timer") -> dict | None:
+    """The GPU backend on exactly the command window ``cpu_window`` times (same setup: inputs prepared, pattern advanced
+    until the live width first reaches its maximum, then ``n_cmds`` consecutive commands)."""
+    import torch
+
+    from graphix_b200.simulator import DefaultMeasureMethod
+
+    cmds = list(pattern)
+    backend.state.reset()
+    backend.node_index.clear()
+    from graphix_b200 import mbqc
+
+    backend.add_nodes(pattern.input_nodes, mbqc.BasicStates.PLUS)
+    mm = DefaultMeasureMethod()
+
+    def run(cmd) -> None:
+        k = cmd.kind.name
+        if k == "N":
+            backend.add_nodes([cmd.node], cmd.state)
+        elif k == "E":
+            backend.entangle_nodes(cmd.nodes)
+        elif k == "M":
+            mm.measure(backend, cmd)
+        elif k in ("X", "Z"):
+            if mm.check_domain(cmd.domain):
+                backend.correct_byproduct(cmd)
+        elif k == "C":
+            backend.apply_clifford(cmd.node, cmd.clifford)
+
+    pos = 0
+    while backend.nqubit < pattern.max_space() and pos < len(cmds):
+        run(cmds[pos])
+        pos += 1
+    if pos + n_cmds > len(cmds):
+        return None
+    backend.state.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timer.barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for c in cmds[pos:pos + n_cmds]:
+        run(c)
+    backend.state.sync()          # queued projections of the window are executed and checked inside the timed region
+    e1.record()
+    timer.barrier()
+    ms = max(e0.elapsed_time(e1), 0.0)
+    wall = (time.perf_counter() - t0) * 1e3
+    return {"value": n_cmds / (max(ms, 1e-6) * 1e-3), "unit": UNIT, "ms": ms, "wall_ms": wall,
+            "note": "same commands, same widths, state resident; one window (no warm-up of this window)"}
 
 
 # ---------------------------------------------------------------------------
@@ -569,18 +799,87 @@ def dm_cpu_window(pattern, max_ops: int, budget_s: float = 30.0):
     return done, time.perf_counter() - t0, backend.nqubit
 
 
-def dm_arm(args) -> None:
+def dm_record(args, name: str, steps: int, warmup: int) -> dict:
+    """BASELINE config 5 (noisy pattern on the density-matrix backend, Kraus-channel kernels) as one JSON record:
+    device-resident commands/s, roofline of the dominant kernel, end-to-end (final rho read back to pinned host memory
+    inside the timed region) and the numpy oracle port over a bounded window."""
     import torch
 
     from graphix_b200 import B200DensityMatrixBackend, PatternSimulator, _lib, mbqc
     from graphix_b200.noise import DepolarisingNoiseModel
     from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern
 
-    name = args.workload
     pattern = load_pattern(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
     ncmd = len(pattern)
     width = pattern.max_space()
+    dev = torch.cuda.current_device()
+    backend = B200DensityMatrixBackend.with_capacity(width, branch_selector=mbqc.ConstBranchSelector(0), device=dev)
+    nm = DepolarisingNoiseModel(**DM_NOISE)
+
+    def one_step() -> None:
+        backend.state.reset()
+        backend.node_index.clear()
+        PatternSimulator(pattern, backend, noise_model=nm).run(rng=np.random.default_rng(7))
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize()
+    backend.state.reset_stats()
+    backend.state.set_option(_lib.OPT_PROFILE, 1)
+    sampler = ClockSampler(dev)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    stats = {k: v for k, v in backend.state.stats().items() if v["launches"]}
+    backend.state.set_option(_lib.OPT_PROFILE, 0)
+    # end to end: the noisy run plus the read-back of the final density matrix to host memory
+    n_out = len(pattern.output_nodes)
+    one_step()
+    _ = backend.state.rho
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+        rho = backend.state.rho
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    tr = float(np.trace(rho).real)
+    cpu = None
+    if not args.no_cpu:
+        done, dt, nq = dm_cpu_window(pattern, args.cpu_window or 10 ** 9, budget_s=15.0)
+        cpu = {"value": done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {done} commands of {name} (+ noise channels) in {dt:.1f} s on the numpy density-matrix "
+                         f"oracle, register grown to {nq} of {width} qubits"}
+    rec = {
+        "metric": METRIC, "value": ncmd * steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps,
+        "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": name, "backend": "densitymatrix", "commands_per_step": ncmd, "live_qubits": width,
+                   "rho_bytes_max": 16 << (2 * width), "noise": DM_NOISE, "selector": "ConstBranchSelector(0)",
+                   "rng": "default_rng(7)", "l2": "rho >> 126 MB L2 at full width"},
+        "e2e": {"value": ncmd * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 << (2 * n_out),
+                "ms_per_step": e2e_s * 1e3 / steps, "final_trace": tr,
+                "note": "inputs are |+> product states (no upload); the final rho is read back to host memory every step"},
+        "gpu_launches": int(sum(v["launches"] for v in stats.values())),
+        "roofline": roofline_of(stats, dev_ms), "cpu_baseline": cpu, "clocks": clocks,
+        "kernels": kernel_table(stats, steps, measured_peak()[0]),
+    }
+    del backend
+    return rec
+
+
+def dm_arm(args) -> None:
+    from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern
+
+    name = args.workload
     if args.impl == "reference":
+        pattern = load_pattern(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
         done, dt, nq = dm_cpu_window(pattern, args.cpu_window or 10 ** 9, budget_s=60.0)
         value = done / dt
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1,
@@ -593,61 +892,10 @@ def dm_arm(args) -> None:
                           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}))
         return
+    import torch
+
     torch.cuda.set_device(0)
-    backend = B200DensityMatrixBackend.with_capacity(width, branch_selector=mbqc.ConstBranchSelector(0), device=0)
-    nm = DepolarisingNoiseModel(**DM_NOISE)
-
-    def one_step() -> None:
-        backend.state.reset()
-        backend.node_index.clear()
-        PatternSimulator(pattern, backend, noise_model=nm).run(rng=np.random.default_rng(7))
-
-    for _ in range(args.warmup):
-        one_step()
-    torch.cuda.synchronize()
-    backend.state.reset_stats()
-    backend.state.set_option(_lib.OPT_PROFILE, 1)
-    sampler = ClockSampler(0)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        one_step()
-    e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    dev_ms = e0.elapsed_time(e1)
-    stats = {k: v for k, v in backend.state.stats().items() if v["launches"]}
-    peak, peak_src = measured_peak()
-    dom = max(stats, key=lambda k: stats[k]["device_ms"])
-    d = stats[dom]
-    total_ms = sum(v["device_ms"] for v in stats.values())
-    total_bytes = sum(v["algo_bytes"] for v in stats.values())
-    cpu = None
-    if not args.no_cpu:
-        done, dt, nq = dm_cpu_window(pattern, args.cpu_window or 10 ** 9, budget_s=30.0)
-        cpu = {"value": done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"first {done} commands of {name} (+ noise channels) in {dt:.1f} s on the numpy density-matrix "
-                         f"oracle, register grown to {nq} of {width} qubits"}
-    line = {
-        "metric": METRIC, "value": ncmd * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": {"workload": name, "backend": "densitymatrix", "commands_per_step": ncmd, "live_qubits": width,
-                   "rho_bytes_max": 16 << (2 * width), "noise": DM_NOISE, "selector": "ConstBranchSelector(0)",
-                   "rng": "default_rng(7)", "l2": "rho >> 126 MB L2 at full width"},
-        "e2e": None, "gpu_launches": int(sum(v["launches"] for v in stats.values())),
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": d["algo_bytes"] / (d["device_ms"] * 1e-3) / 1e9,
-                     "peak": peak, "unit": "GB/s", "frac": d["algo_bytes"] / (d["device_ms"] * 1e-3) / 1e9 / peak,
-                     "peak_source": peak_src, "traffic": None, "share_of_kernel_time": d["device_ms"] / total_ms,
-                     "all_kernels_frac": total_bytes / (total_ms * 1e-3) / 1e9 / peak,
-                     "kernel_time_share_of_step": total_ms / dev_ms},
-        "cpu_baseline": cpu, "clocks": clocks,
-        "kernels": {k: {"launches_per_step": v["launches"] / args.steps, "ms_per_launch": v["device_ms"] / v["launches"],
-                        "GBps": v["algo_bytes"] / (v["device_ms"] * 1e-3) / 1e9 if v["device_ms"] else None}
-                    for k, v in stats.items()},
-    }
-    print(json.dumps(line))
+    print(json.dumps(dm_record(args, name, args.steps, args.warmup)))
 
 
 def main() -> None:
@@ -674,6 +922,11 @@ def main() -> None:
     ap.set_defaults(nonstrict=True)
     ap.add_argument("--cpu-window", type=int, default=0, help="commands per CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="default run only: skip the config3 / config4 / config5 sub-records")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the in-run parity checks (sharded golden traces, complete QFT run of config 4)")
+    ap.add_argument("--config4-window", type=int, default=900, help="commands of the timed config 4 prefix window")
     args = ap.parse_args()
     if args.workload and args.workload.startswith(("config5", "dm_")):
         dm_arm(args)

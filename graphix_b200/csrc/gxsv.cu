@@ -31,7 +31,7 @@ constexpr int TILE_BITS = 11;   // k_contract<4,true>: a CTA tile spans the lowe
 constexpr int U_DEF = 4;
 constexpr int RING = 4096;    // result slots (128 B each, pinned + mapped)
 constexpr int GXSV_VERSION = 100;
-constexpr int MAX_BATCH_AXES = 5;  // distinct physical bits one batched pass may act on (GXSV_BATCH_AXES = 1..6).
+constexpr int MAX_BATCH_AXES = 6;  // distinct physical bits one batched pass may act on (GXSV_BATCH_AXES = 1..6).
 // Up to 3 axes run in k_fused_batch (2^3 amplitudes per thread in registers, 4 CTAs per SM); 4..6 axes run in
 // k_fused_tile, which keeps three axes at a time in registers and transposes the CTA tile through shared memory
 // between phases.  (Round 1 measured a 4-axis all-register pass: 128 registers, 2 CTAs per SM, 0.64 of the copy rate.)
@@ -251,24 +251,29 @@ int check_launch(gxsv_t* h, const char* what) {
   return GXSV_OK;
 }
 
-// bit lo of the result = parity of (the physical bits of the register axes selected by lo) & mask
-unsigned char parity_table(uint64_t mask, const unsigned char* regbit, int nb) {
+// Sign table of a stage acting on register axis `la` of `nb` register axes (physical bits regbit[]): byte k = 0x80 iff
+// the k-th amplitude pair (slot lo = k with a zero bit inserted at position la) has odd parity of
+// (physical bits of the register axes set in lo) & mask.
+unsigned int parity_table(uint64_t mask, const unsigned char* regbit, int nb, int la) {
   unsigned int t = 0;
-  for (int lo = 0; lo < (1 << nb); ++lo) {
+  for (int k = 0; k < (1 << (nb - 1)); ++k) {
+    const int lo = ((k >> la) << (la + 1)) | (k & ((1 << la) - 1));
     int par = 0;
     for (int i = 0; i < nb; ++i)
       if (((lo >> i) & 1) && ((mask >> regbit[i]) & 1ull)) par ^= 1;
-    t |= (unsigned int)par << lo;
+    if (par) t |= 0x80u << (8 * k);
   }
-  return (unsigned char)t;
+  return t;
 }
 
 // Greedy phase plan of a batch on more than three axes: every phase is the longest run of consecutive stages that
 // acts on at most three distinct batch axes (those are held in registers, k_fused_tile).  Returns the number of
-// phases (out may be NULL: the queueing code only asks whether one more stage still fits MAX_PHASES).
+// phases (out may be NULL: the queueing code only asks whether one more stage still fits MAX_PHASES).  With `out`,
+// also tabulates the offsets the kernel addresses with.
 int plan_phases(const Batch& bt, TileBatch* out) {
   int nph = 0;
   int i = 0;
+  const int A = bt.naxes, F = WTILE_LOG2 - A;
   while (i < bt.nstages) {
     int T[3], nt = 0, j = i;
     for (; j < bt.nstages; ++j) {
@@ -281,28 +286,40 @@ int plan_phases(const Batch& bt, TileBatch* out) {
     }
     if (out && nph < MAX_PHASES) {
       // pad the register set to three axes with batch axes that the phase does not use
-      for (int a = 0; a < bt.naxes && nt < 3; ++a) {
+      for (int a = 0; a < A && nt < 3; ++a) {
         bool in = false;
         for (int k = 0; k < nt; ++k) in = in || (T[k] == a);
         if (!in) T[nt++] = a;
       }
       std::sort(T, T + 3);
-      Phase& ph = out->ph[nph];
-      int no = 0;
-      for (int a = 0; a < bt.naxes; ++a) {
-        int slot = -1;
-        for (int k = 0; k < 3; ++k) if (T[k] == a) slot = k;
-        if (slot >= 0) ph.ax[slot] = (unsigned char)a; else ph.oth[no++] = (unsigned char)a;
+      int oth[3], no = 0;
+      for (int a = 0; a < A; ++a) {
+        bool in = false;
+        for (int k = 0; k < 3; ++k) in = in || (T[k] == a);
+        if (!in) oth[no++] = a;
       }
-      for (; no < 3; ++no) ph.oth[no] = 0;
-      ph.s_begin = (unsigned char)i;
-      ph.s_end = (unsigned char)j;
       unsigned char regbit[3];
       for (int k = 0; k < 3; ++k) regbit[k] = bt.axbit[T[k]];
+      for (int b = 0; b < 8; ++b) {
+        uint64_t go = 0;
+        unsigned int so = 0;
+        for (int k = 0; k < 3; ++k)
+          if ((b >> k) & 1) { go |= 1ull << regbit[k]; so |= 1u << T[k]; }
+        out->gbits[nph][b] = go;
+        out->sbits[nph][b] = (unsigned short)(so << F);
+      }
+      for (int k = 0; k < 4; ++k) {
+        out->goth[nph][k] = (k < no) ? (1ull << bt.axbit[oth[k]]) : 0ull;
+        out->soth[nph][k] = (k < no) ? (unsigned short)((1u << oth[k]) << F) : (unsigned short)0;
+      }
+      out->s_begin[nph] = (unsigned char)i;
+      out->s_end[nph] = (unsigned char)j;
       for (int s = i; s < j; ++s) {
-        for (int k = 0; k < 3; ++k) if (T[k] == bt.st[s].axis) out->lax[s] = (unsigned char)k;
-        out->st[s].qtab = parity_table(bt.st[s].mq, regbit, 3);
-        out->st[s].vtab = parity_table(bt.st[s].mv, regbit, 3);
+        int la = 0;
+        for (int k = 0; k < 3; ++k) if (T[k] == bt.st[s].axis) la = k;
+        out->lax[s] = (unsigned char)la;
+        out->st[s].qtab = parity_table(bt.st[s].mq, regbit, 3, la);
+        out->st[s].vtab = parity_table(bt.st[s].mv, regbit, 3, la);
       }
     }
     nph += 1;
@@ -366,9 +383,11 @@ bool plan_tma(const gxsv_t* h, const Batch& bt, TmaBatch* out, Holes* hs) {
       out->st[s2] = bt.st[s2];
       out->nscale[s2] = bt.nscale[s2];
       const int sbit = tile_bit(bt.st[s2].axis);
-      for (int k = 0; k < 3; ++k) if (T[k] == sbit) out->lax[s2] = (unsigned char)k;
-      out->st[s2].qtab = parity_table(bt.st[s2].mq, regbit, 3);
-      out->st[s2].vtab = parity_table(bt.st[s2].mv, regbit, 3);
+      int la = 0;
+      for (int k = 0; k < 3; ++k) if (T[k] == sbit) la = k;
+      out->lax[s2] = (unsigned char)la;
+      out->st[s2].qtab = parity_table(bt.st[s2].mq, regbit, 3, la);
+      out->st[s2].vtab = parity_table(bt.st[s2].mv, regbit, 3, la);
     }
     nph += 1;
     i = j;
@@ -432,8 +451,8 @@ int flush_batch(gxsv_t* h) {
     k_fused_tma<<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, g_tma_holes, g_tma, ntiles, h->partials, h->ctrl, slot, seq, fm);
   } else if (bt.naxes <= 3) {
     for (int k = 0; k < bt.nstages; ++k) {
-      bt.st[k].qtab = parity_table(bt.st[k].mq, bt.axbit, bt.naxes);
-      bt.st[k].vtab = parity_table(bt.st[k].mv, bt.axbit, bt.naxes);
+      bt.st[k].qtab = parity_table(bt.st[k].mq, bt.axbit, bt.naxes, bt.st[k].axis);
+      bt.st[k].vtab = parity_table(bt.st[k].mv, bt.axbit, bt.naxes, bt.st[k].axis);
     }
     Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
     // chunked CTA -> index mapping only when every CTA still gets >= 8 chunks (else plain grid stride)
@@ -447,7 +466,6 @@ int flush_batch(gxsv_t* h) {
     memset(&tb, 0, sizeof tb);
     tb.nstages = bt.nstages;
     tb.naxes = bt.naxes;
-    for (int a = 0; a < bt.naxes; ++a) tb.axbit[a] = bt.axbit[a];
     for (int k = 0; k < bt.nstages; ++k) { tb.st[k] = bt.st[k]; tb.nscale[k] = bt.nscale[k]; }
     tb.nphases = plan_phases(bt, &tb);
     if (tb.nphases > MAX_PHASES) return fail(h, GXSV_EVALUE, "internal: batch needs %d phases", tb.nphases);
@@ -1358,7 +1376,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           if (ax < 0) { ax = h->batch.naxes++; h->batch.axbit[ax] = (unsigned char)p; }
           Stage& st = h->batch.st[h->batch.nstages++];
           st.m00 = d2(s0 * c0); st.m01 = d2(s0 * c1); st.m10 = d2(s1 * c0); st.m11 = d2(-s1 * c1);
-          st.mq = mq; st.mv = mv; st.axis = ax; st.qtab = st.vtab = 0;
+          st.mq = mq; st.mv = mv; st.axis = ax; st.qtab = st.vtab = 0; st.pad = 0;
           // |+> / |-> partners (s1 = +-s0): take the scalar f = s0 * c_pivot out of the stage (Stage kinds 0 / 1 in
           // kernels.cuh).  Its phase (sharded: f itself, so that the all-reduced norms stay those of the true state)
           // stays in the host scalar, |f|^2 goes into the published norms.  A sharded state may carry a rank-dependent

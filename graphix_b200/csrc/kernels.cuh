@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace gxk {
 
@@ -393,7 +394,8 @@ constexpr int MAX_STAGES = 8;
 //   r0 = t0 + a t1, r1 = +-sv (t0 - a t1), a = c1/c0      (kind 0)       one complex multiply, four additions
 //   r0 = a t0 + t1, r1 = +-sv (a t0 - t1), a = c0/c1      (kind 1)       (12 FP64 operations per pair instead of 21).
 // The CZ signs are sign-bit XORs: the parity of the thread's fixed index bits is taken once per stage and combined with
-// a host-made 8-bit table (qtab / vtab: parity contributed by the register-axis bits of slot `lo`).
+// a host-made table (qtab / vtab: parity contributed by the register-axis bits of the k-th pair, one byte per pair,
+// flag in the byte's top bit so that one byte permute yields the 0 / 0x80000000 mask of a pair).
 struct Stage {
   double2 m00, m01, m10, m11;    // the unfactored 2x2 (kind 2; also what a batch of one hands to k_fused)
   double2 a;                     // kinds 0 / 1: the one multiplier left after taking f out
@@ -401,7 +403,9 @@ struct Stage {
   int axis;                      // batch axis index
   unsigned char kind;            // 0 / 1 / 2, see above
   unsigned char neg;             // kinds 0/1: s1 = -s0
-  unsigned char qtab, vtab;      // set when the pass is launched (depend on the register assignment of the axes)
+  unsigned short pad;
+  unsigned int qtab, vtab;       // set when the pass is launched (depend on the register assignment of the axes):
+                                 // byte k = 0x80 iff the k-th amplitude pair of the stage's axis takes the sign
 };
 struct Batch {
   int nstages;
@@ -420,16 +424,17 @@ __device__ __forceinline__ double flip_sign(const double x, const unsigned int s
 template <int NB, int AX>
 __device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage& st, const unsigned int gpar_q,
                                               const unsigned int gpar_v, double& nrm0, double& nrm1) {
-  // bit lo of tq / tv = 1 iff the amplitude pair of slot lo takes the sign
-  const unsigned int tq = (gpar_q & 1u) ? ~(unsigned int)st.qtab : (unsigned int)st.qtab;
-  const unsigned int tv = ((gpar_v ^ st.neg) & 1u) ? ~(unsigned int)st.vtab : (unsigned int)st.vtab;
+  // byte k of tq / tv = 0x80 iff the k-th amplitude pair takes the sign
+  const unsigned int tq = st.qtab ^ ((gpar_q & 1u) ? 0x80808080u : 0u);
+  const unsigned int tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x80808080u : 0u);
   const double2 a = st.a;
   if (st.kind == 0) {
 #pragma unroll
     for (int lo = 0; lo < (1 << NB); ++lo) {
       if ((lo >> AX) & 1) continue;
       const int hi = lo | (1 << AX);
-      const unsigned int sq = (tq << (31 - lo)) & 0x80000000u, sv = (tv << (31 - lo)) & 0x80000000u;
+      const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded)
+      const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | (k << 12)), sv = __byte_perm(tv, 0u, 0x0444 | (k << 12));
       double2 w = cmul(a, v[hi]);
       w.x = flip_sign(w.x, sq);
       w.y = flip_sign(w.y, sq);
@@ -445,7 +450,8 @@ __device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage
     for (int lo = 0; lo < (1 << NB); ++lo) {
       if ((lo >> AX) & 1) continue;
       const int hi = lo | (1 << AX);
-      const unsigned int sq = (tq << (31 - lo)) & 0x80000000u, sv = (tv << (31 - lo)) & 0x80000000u;
+      const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded)
+      const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | (k << 12)), sv = __byte_perm(tv, 0u, 0x0444 | (k << 12));
       const double2 u = cmul(a, v[lo]);
       const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
       const double2 r0 = make_double2(u.x + t1.x, u.y + t1.y);
@@ -461,7 +467,8 @@ __device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage
     for (int lo = 0; lo < (1 << NB); ++lo) {
       if ((lo >> AX) & 1) continue;
       const int hi = lo | (1 << AX);
-      const unsigned int sq = (tq << (31 - lo)) & 0x80000000u, sv = (tv << (31 - lo)) & 0x80000000u;
+      const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded)
+      const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | (k << 12)), sv = __byte_perm(tv, 0u, 0x0444 | (k << 12));
       const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
       const double2 r0 = cmad2(m00, v[lo], m01, t1);
       double2 r1 = cmad2(m10, v[lo], m11, t1);
@@ -550,16 +557,15 @@ constexpr int TILE_LOG2 = 11;      // amplitudes per CTA iteration
 constexpr int WTILE_LOG2 = 8;      // amplitudes per warp tile
 constexpr int MAX_TILE_AXES = 6;
 constexpr int MAX_PHASES = 4;
-struct Phase {
-  unsigned char ax[3];    // batch-axis indices held in registers during this phase
-  unsigned char oth[3];   // the remaining naxes - 3 batch axes (their values are fixed per thread)
-  unsigned char s_begin, s_end;
-};
 struct TileBatch {
   int nstages, naxes, nphases, pad;
-  unsigned char axbit[8];          // physical bit of every batch axis
-  unsigned char lax[MAX_STAGES];   // register slot (0..2) of the axis of every stage inside its phase
-  Phase ph[MAX_PHASES];
+  unsigned char lax[MAX_STAGES];              // register slot (0..2) of the axis of every stage inside its phase
+  unsigned char s_begin[MAX_PHASES], s_end[MAX_PHASES];
+  // everything a thread needs to address its 2^3 amplitudes is tabulated by the host (no per-tile index arithmetic):
+  unsigned long long gbits[MAX_PHASES][8];    // physical offset of register slot b in phase p
+  unsigned long long goth[MAX_PHASES][4];     // physical offset of the i-th axis fixed per lane (taken iff bit i of r = lane >> F)
+  unsigned short sbits[MAX_PHASES][8];        // the same two as offsets inside the warp's shared-memory tile (<< F applied)
+  unsigned short soth[MAX_PHASES][4];
   double nscale[MAX_STAGES];
   Stage st[MAX_STAGES];
 };
@@ -569,12 +575,13 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi
                                                       Res* res, const unsigned long long seq, const int fin_mode) {
   extern __shared__ double2 tile_all[];             // 8 warps x 2^WTILE_LOG2 amplitudes (dynamic: 32 KB)
   __shared__ double sacc[MAX_STAGES][TPB];
-  const int A = bt.naxes, F = WTILE_LOG2 - A;
+  const int F = WTILE_LOG2 - bt.naxes;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double2* tile = tile_all + ((size_t)warp << WTILE_LOG2);
   const unsigned int f = lane & ((1u << F) - 1u);
   const int r = lane >> F;
   const double g = ctrl->g;
+  const int nphases = bt.nphases;
 #pragma unroll
   for (int k = 0; k < MAX_STAGES; ++k) sacc[k][tid] = 0.0;
   const uint64_t nchunks = (ntiles + (1ull << glog) - 1ull) >> glog;
@@ -585,47 +592,30 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi
       const uint64_t wt = t * (TPB / 32) + warp;    // this warp's tile
       const uint64_t base = expand((wt << F) | f, hs);
       double2 v[8];
-      for (int p = 0; p < bt.nphases; ++p) {
-        const Phase& ph = bt.ph[p];
-        uint64_t gthread = base;                    // physical index of this thread's group (register axes = 0)
-        unsigned int sthread = 0;                   // same, as axis-combination index of the warp's shared-memory tile
-        for (int i = 0; i < A - 3; ++i)
-          if ((r >> i) & 1) {
-            gthread |= 1ull << bt.axbit[ph.oth[i]];
-            sthread |= 1u << ph.oth[i];
-          }
-        uint64_t gax[3];
-        unsigned int sax[3];
+      // offsets of the axis values fixed per lane: uniform table entries selected by the bits of r (a table indexed by
+      // r itself — a per-thread index into the kernel parameters — faulted on sm_100a with CUDA 12.9 although the
+      // emulated addresses were all in range; the uniform form costs three predicated ORs)
+      auto lane_off = [&](int p, uint64_t& go, unsigned int& so) {
+        go = base;
+        so = f;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          gax[i] = 1ull << bt.axbit[ph.ax[i]];
-          sax[i] = 1u << ph.ax[i];
+        for (int i = 0; i < 3; ++i)
+          if ((r >> i) & 1) { go |= bt.goth[p][i]; so |= bt.soth[p][i]; }
+      };
+      uint64_t gthread;
+      unsigned int sthread;
+      lane_off(0, gthread, sthread);
+      {
+        double2* src = psi + gthread;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const double2 a = ld_amp(src + bt.gbits[0][b]);
+          v[b] = make_double2(g * a.x, g * a.y);    // the pending normalisation, once per pass
         }
-        auto goff = [&](int b) {
-          uint64_t o = 0;
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-            if ((b >> i) & 1) o |= gax[i];
-          return o;
-        };
-        auto soff = [&](int b) {
-          unsigned int o = sthread;
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-            if ((b >> i) & 1) o |= sax[i];
-          return (o << F) | f;
-        };
-        if (p == 0) {
-#pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const double2 a = ld_amp(psi + gthread + goff(b));
-            v[b] = make_double2(g * a.x, g * a.y);  // the pending normalisation, once per pass
-          }
-        } else {
-#pragma unroll
-          for (int b = 0; b < 8; ++b) v[b] = tile[soff(b)];
-        }
-        for (int s = ph.s_begin; s < ph.s_end; ++s) {
+      }
+      for (int p = 0; p < nphases; ++p) {
+        // gthread = physical index of this thread's group (register axes = 0), sthread = its slot base in the warp tile
+        for (int s = bt.s_begin[p]; s < bt.s_end[p]; ++s) {
           const Stage& st = bt.st[s];
           const unsigned int pq = __popcll(gthread & st.mq), pv = __popcll(gthread & st.mv);
           double n0 = 0.0, n1 = 0.0;
@@ -635,14 +625,21 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi
           else stage_on_axis<3, 2>(v, st, pq, pv, n0, n1);
           sacc[s][tid] += n0 + n1;
         }
-        if (p + 1 < bt.nphases) {
+        if (p + 1 < nphases) {
+          // transpose through the warp's private tile to the register assignment of the next phase
+          const unsigned int s_old = sthread;
+          lane_off(p + 1, gthread, sthread);
+          const unsigned int s_new = sthread;
           __syncwarp();                             // every lane has read its slots of the previous transpose
 #pragma unroll
-          for (int b = 0; b < 8; ++b) tile[soff(b)] = v[b];
+          for (int b = 0; b < 8; ++b) tile[s_old | bt.sbits[p][b]] = v[b];
           __syncwarp();
-        } else {
 #pragma unroll
-          for (int b = 0; b < 8; ++b) st_amp(psi + gthread + goff(b), v[b]);
+          for (int b = 0; b < 8; ++b) v[b] = tile[s_new | bt.sbits[p + 1][b]];
+        } else {
+          double2* dst = psi + gthread;
+#pragma unroll
+          for (int b = 0; b < 8; ++b) st_amp(dst + bt.gbits[p][b], v[b]);
         }
       }
     }
