@@ -183,6 +183,31 @@ def cpu_window(pattern, n_cmds: int, steps: int, warmup: int):
     return times
 
 
+def host_window(name: str, pattern, n_cmds: int, steps: int, warmup: int, force_port: bool = False):
+    """The reference's CPU implementation of the path over a bounded window: the REAL reference (graphix numba backend,
+    oracle/ref_runner.py; kind "reference") when it can be imported here, else the C/OpenMP port of the oracle (kind "port").
+    Returns (times, kind, cores, note)."""
+    if not force_port:
+        try:
+            from oracle import ref_runner
+
+            ok, why = ref_runner.available()
+            if ok:
+                from graphix_b200.pattern_io import GOLDEN_DIR, load_pattern_dict
+
+                d = load_pattern_dict(os.path.join(GOLDEN_DIR, "patterns", name + ".json.gz"))
+                times, threads = ref_runner.time_window(d, n_cmds, steps, warmup)
+                return times, "reference", threads, "graphix StatevectorBackend (numba kernels), numba threads = %d" % threads
+            note = why
+        except Exception as exc:  # noqa: BLE001
+            note = f"{type(exc).__name__}: {exc}"
+    else:
+        note = "forced"
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    return cpu_window(pattern, n_cmds, steps, warmup), "port", cores, "C/OpenMP port of the reference kernels (real reference unavailable: %s)" % note
+
+
 def reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -195,22 +220,21 @@ def reference_arm(args) -> None:
         print(json.dumps({"impl": "reference", "metric": METRIC, "unit": UNIT, "value": None, "n_gpus": args.gpus,
                           "unavailable": "reference is limited to 31 qubits (int32 kernel signatures, SURVEY.md §2.1)"}))
         return
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     width = pattern.max_space()
     n_cmds = args.cpu_window or max(3, min(30, int(round(12 * 2.0 ** (27 - width)))) if width >= 24 else 300)
-    times = cpu_window(pattern, n_cmds, args.steps, args.warmup)
+    times, kind, cores, note = host_window(name, pattern, n_cmds, args.steps, args.warmup, force_port=args.port)
     if not times:
         raise SystemExit("pattern too short for the requested window")
     per_step = float(np.mean(times))
     value = n_cmds / per_step
-    sample = f"{n_cmds} consecutive commands of {name} per step at {width - 1}<->{width} live qubits (bounded window)"
+    sample = (f"{n_cmds} consecutive commands of {name} per step at {width - 1}<->{width} live qubits (bounded window); "
+              f"{note}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic",
         "config": {"workload": name, "selector": "ConstBranchSelector(0)", "commands_per_step": n_cmds},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -412,13 +436,12 @@ def config3_record(args, timer: Timer, local_rank: int) -> dict:
     del b
     free_device_memory()
     if not args.no_cpu:
-        cores = os.cpu_count() or 1
         n_cmds = 8
-        times = cpu_window(pattern, n_cmds, 1, 0)
+        times, kind, cores, note = host_window(name, pattern, n_cmds, 1, 0, force_port=args.port)
         if times:
-            out["cpu_baseline"] = {"value": n_cmds / times[0], "unit": UNIT, "cores": cores, "kind": "port",
+            out["cpu_baseline"] = {"value": n_cmds / times[0], "unit": UNIT, "cores": cores, "kind": kind,
                                    "sample": f"{n_cmds} consecutive commands of {name} at {width - 1}<->{width} live "
-                                             f"qubits, {times[0]:.1f} s of CPU work"}
+                                             f"qubits, {times[0]:.1f} s of CPU work; {note}"}
     return out
 
 
@@ -654,12 +677,11 @@ def gpu_arm(args) -> None:
     # ---- CPU baseline: the oracle port on this box's cores, bounded window --------
     cpu_baseline = None
     if cpu_n:
-        cores = os.cpu_count() or 1
-        times = cpu_window(pattern, cpu_n, 1, 0)
+        times, kind, cores, note = host_window(name, pattern, cpu_n, 1, 0, force_port=args.port)
         if times:
-            cpu_baseline = {"value": cpu_n / times[0], "unit": UNIT, "cores": cores, "kind": "port",
+            cpu_baseline = {"value": cpu_n / times[0], "unit": UNIT, "cores": cores, "kind": kind,
                             "sample": f"{cpu_n} consecutive commands of {name} at {width - 1}<->{width} live qubits, "
-                                      f"{times[0]:.1f} s of CPU work",
+                                      f"{times[0]:.1f} s of CPU work; {note}",
                             "gpu_same_window": same_window}
 
     line = {
@@ -852,7 +874,7 @@ def dm_record(args, name: str, steps: int, warmup: int) -> dict:
     tr = float(np.trace(rho).real)
     cpu = None
     if not args.no_cpu:
-        done, dt, nq = dm_cpu_window(pattern, args.cpu_window or 10 ** 9, budget_s=15.0)
+        done, dt, nq = dm_cpu_window(pattern, args.cpu_window or 1, budget_s=15.0)
         cpu = {"value": done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": f"first {done} commands of {name} (+ noise channels) in {dt:.1f} s on the numpy density-matrix "
                          f"oracle, register grown to {nq} of {width} qubits"}
@@ -922,6 +944,8 @@ def main() -> None:
     ap.set_defaults(nonstrict=True)
     ap.add_argument("--cpu-window", type=int, default=0, help="commands per CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--port", action="store_true",
+                    help="CPU legs: time the C/OpenMP port of the oracle even when the real reference is importable")
     ap.add_argument("--no-extra", action="store_true",
                     help="default run only: skip the config3 / config4 / config5 sub-records")
     ap.add_argument("--no-parity", action="store_true",

@@ -106,6 +106,9 @@ struct gxsv {
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   std::string err;
+  // peer registers of the ranks this shard exchanges with (CUDA IPC mappings, one slot per rank-index bit)
+  double2* peer_psi[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double2* exported_psi = nullptr;
 };
 
 static thread_local std::string g_err;
@@ -905,6 +908,7 @@ int gxsv_destroy(gxsv_t* h) {
   if (h->op_dev) cudaFree(h->op_dev);
   if (h->ring_host) cudaFreeHost(h->ring_host);
   for (int i = 0; i < 2; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
+  for (int i = 0; i < 8; ++i) if (h->peer_psi[i]) cudaIpcCloseMemHandle(h->peer_psi[i]);
   delete h;
   return GXSV_OK;
 }
@@ -1774,6 +1778,63 @@ int gxsv_pack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count,
 int gxsv_unpack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, const void* in_device,
                      double re, double im) {
   return pack_common(h, q, bitval, first, count, (void*)in_device, false, re, im);
+}
+
+// ---- peer-memory exchange (CUDA IPC over NVLink) --------------------------------------------------------------
+int gxsv_ipc_export(gxsv_t* h, unsigned char out[64]) {
+  CU(cudaSetDevice(h->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  CU(cudaIpcGetMemHandle(&hd, h->psi));
+  memcpy(out, &hd, 64);
+  h->exported_psi = h->psi;
+  return GXSV_OK;
+}
+
+int gxsv_ipc_open(gxsv_t* h, int slot, const unsigned char handle[64]) {
+  CU(cudaSetDevice(h->device));
+  if (slot < 0 || slot >= 8) return fail(h, GXSV_EVALUE, "ipc_open: slot %d out of range", slot);
+  if (h->peer_psi[slot]) { cudaIpcCloseMemHandle(h->peer_psi[slot]); h->peer_psi[slot] = nullptr; }
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  void* p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+  h->peer_psi[slot] = (double2*)p;
+  return GXSV_OK;
+}
+
+int gxsv_ipc_close(gxsv_t* h) {
+  cudaSetDevice(h->device);
+  for (int i = 0; i < 8; ++i)
+    if (h->peer_psi[i]) { cudaIpcCloseMemHandle(h->peer_psi[i]); h->peer_psi[i] = nullptr; }
+  return GXSV_OK;
+}
+
+int gxsv_swap_peer(gxsv_t* h, int q, int slot, int my_bit, double fre, double fim) {
+  CU(cudaSetDevice(h->device));
+  int rc = check_q(h, q);
+  if (rc) return rc;
+  if (slot < 0 || slot >= 8 || !h->peer_psi[slot]) return fail(h, GXSV_EVALUE, "swap_peer: no peer register in slot %d", slot);
+  if (h->exported_psi != h->psi) return fail(h, GXSV_EVALUE, "swap_peer: the register moved since it was exported");
+  if (h->q[q].phys < 0 || has_edge(h, h->q[q].id)) return fail(h, GXSV_EVALUE, "swap_peer: qubit %d must be settled first", q);
+  rc = flush_batch(h);
+  if (rc) return rc;
+  const int p = h->q[q].phys;
+  const uint64_t half = 1ull << (nlive_bits(h) - 1);
+  const int B = my_bit ? 1 : 0;
+  // the two ranks of a pair split the index range: bit 0 takes the lower part, bit 1 the upper part
+  const uint64_t first = B ? half / 2 : 0, count = B ? half - half / 2 : half / 2;
+  if (count == 0) return GXSV_OK;
+  Holes hs = make_holes(h, p);
+  const uint64_t my_or = (uint64_t)(1 - B) << p, peer_or = (uint64_t)B << p;
+  const cplx f(fre, fim), finv = cplx(1.0) / f;
+  const int scale = (f != cplx(1.0, 0.0)) ? 1 : 0;
+  {
+    Launch L(h, GXSV_K_MISC, 64.0 * (double)count);
+    k_swap_peer<U_DEF><<<grid_for(h, count, U_DEF), TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or,
+                                                                       first, count, d2(f), d2(finv), scale);
+  }
+  return check_launch(h, "k_swap_peer");
 }
 
 int gxsv_sync(gxsv_t* h) {

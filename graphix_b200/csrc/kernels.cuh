@@ -1124,6 +1124,46 @@ __global__ void __launch_bounds__(TPB) k_unpack_half(double2* __restrict__ psi, 
 }
 
 // ---------------------------------------------------------------------------
+// Sharded states, peer-memory exchange (one process per GPU, the partner's register mapped through CUDA IPC over
+// NVLink / NVSwitch).  Swapping the rank-index qubit on rank bit k with the local qubit on physical bit p exchanges, between
+// the two ranks that differ in bit k, the half with bit p = 1 - B of the rank whose bit k is B with the half with bit
+// p = B of its partner, element by element:
+//     mine[e(i) | my_or]  <->  peer[e(i) | peer_or]          (each scaled by the ratio of the ranks' bookkeeping scalars)
+// Each rank runs this kernel over ITS half of the index range [first, first + count), so every pair is touched by exactly
+// one thread of one GPU: in place on both sides, no staging buffers, no pack / unpack passes, and the NVLink traffic of
+// a rank is count * 16 B of loads plus count * 16 B of stores in each direction.  The host brackets the launch with two
+// stream-ordered cross-rank barriers (graphix_b200/sharded.py).
+// ---------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(TPB) k_swap_peer(double2* __restrict__ mine, double2* __restrict__ peer,
+                                                   const __grid_constant__ Holes hs, const uint64_t my_or,
+                                                   const uint64_t peer_or, const uint64_t first, const uint64_t count,
+                                                   const double2 f_mine, const double2 f_peer, const int scale) {
+  const uint64_t chunk = (uint64_t)TPB * U;
+  for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < count; base += (uint64_t)gridDim.x * chunk) {
+    double2 a[U], b[U];
+    uint64_t e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
+      e[u] = expand(first + k, hs);
+      if (k < count) {
+        b[u] = ld_amp(peer + (e[u] | peer_or));      // NVLink load
+        a[u] = ld_amp(mine + (e[u] | my_or));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
+      if (k < count) {
+        st_amp(peer + (e[u] | peer_or), scale ? cmul(f_peer, a[u]) : a[u]);   // NVLink store
+        st_amp(mine + (e[u] | my_or), scale ? cmul(f_mine, b[u]) : b[u]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // general add_nodes: psi[i | spread(j)] = v[j] * psi[i] for j = 1 .. 2^k-1
 // (the j = 0 term is applied afterwards with k_scale_all).  `newbits` lists the
 // physical bit of each new qubit, MSB (first new qubit) first.

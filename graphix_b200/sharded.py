@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from collections.abc import Sequence
 
 import numpy as np
@@ -49,7 +50,9 @@ class GpuShardEngine:
         self.sv = B200Statevector(nqubit=0, max_qubits=local_bits, device=device, fusion=2, strict=strict,
                                   batch=0 if strict else batch)
         self.sv.set_option(_lib.OPT_DIST, 1)
-        self.capacity = local_bits
+        # what was really allocated: the constructor may have fallen back to half the requested register (lazy fusion
+        # rarely needs the last qubit); qubits beyond it go to free rank bits instead of failing later
+        self.capacity = self.sv.max_qubits
         self.device = torch.device("cuda", self.sv._device)
         self._lib = self.sv._lib
         self._h = self.sv._h
@@ -126,6 +129,24 @@ class GpuShardEngine:
         self.sv._check(self._lib.gxsv_unpack_half(self._h, q, bit, first, count, C.c_void_p(src.data_ptr()),
                                                   factor.real, factor.imag))
 
+    # peer-memory exchange (CUDA IPC over NVLink): see include/gxsv.h
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.sv._check(self._lib.gxsv_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_open(self, slot: int, handle: bytes) -> None:
+        self.sv._check(self._lib.gxsv_ipc_open(self._h, slot, handle))
+
+    def ipc_close(self) -> None:
+        self._lib.gxsv_ipc_close(self._h)
+
+    def swap_peer(self, q: int, slot: int, my_bit: int, factor: complex) -> None:
+        self.sv._check(self._lib.gxsv_swap_peer(self._h, q, slot, my_bit, factor.real, factor.imag))
+
+    def stream_handle(self) -> int:
+        return self.sv._stream
+
     def norm2_local(self) -> float:
         return self.sv.norm2()
 
@@ -188,7 +209,42 @@ class ShardedStatevector:
         self.exchange_ms = 0.0
         self.exchange_host_ms = 0.0
         self.sync_wait_ms = 0.0         # host time spent waiting for the device at deferred-check points
+        self.transport = "nccl send/recv (pack -> staging -> unpack)"
+        self._bar = None
+        self._setup_peer_exchange()
         self._clear()
+
+    def _setup_peer_exchange(self) -> None:
+        """Map the partner ranks' registers (CUDA IPC) so that a qubit swap is ONE in-place kernel over NVLink on each
+        side instead of pack -> ncclSend/Recv -> unpack through staging buffers.  All ranks use it or none does."""
+        eng = self.engine
+        if self.P == 1 or not hasattr(eng, "ipc_export") or os.environ.get("GXSV_EXCHANGE", "peer") != "peer":
+            return
+        ok = 1
+        handles = None
+        try:
+            t = torch.frombuffer(bytearray(eng.ipc_export()), dtype=torch.uint8).to(eng.device)
+            handles = [torch.empty_like(t) for _ in range(self.P)]
+            dist.all_gather(handles, t, group=self.group)
+        except Exception:  # noqa: BLE001 - any failure (IPC unsupported, ...) means: keep the NCCL path
+            ok = 0
+        if ok:
+            try:
+                for k in range(self.gbits):
+                    eng.ipc_open(k, bytes(handles[self.rank ^ (1 << k)].cpu().numpy().tobytes()))
+            except Exception:  # noqa: BLE001
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=eng.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self.transport = "peer load/store (CUDA IPC over NVLink), in place, no staging"
+            self._bar = torch.zeros(1, dtype=torch.float32, device=eng.device)
+        else:
+            eng.ipc_close()
+
+    def _stream_barrier(self) -> None:
+        """Cross-rank barrier ordered on the compute stream (no host wait): a one-element all-reduce."""
+        dist.all_reduce(self._bar, group=self.group)
 
     def _clear(self) -> None:
         self.q: list[_Q] = []                      # logical order (reference convention: index 0 = MSB)
@@ -606,6 +662,17 @@ class ShardedStatevector:
             self.engine.scale(complex(self.u[self.rank]))
             self.u[:] = 1.0
         factor = complex(self.u[partner] / self.u[self.rank])
+        if self._bar is not None:
+            # peer-memory path: every rank's earlier kernels are done before anyone touches a partner register, and both
+            # in-place swap kernels are done before anyone goes on
+            if torch.cuda.current_stream().cuda_stream != self.engine.stream_handle():
+                raise RuntimeError("sharded exchange: the current torch stream is not the engine's stream")
+            self._stream_barrier()
+            self.engine.swap_peer(vic.li, k, B, factor)
+            self._stream_barrier()
+            self.exchanged_bytes += 16 * half
+            self._after_swap(glo, vic, k)
+            return
         # large shards: 4+ chunks per exchange so that packing / unpacking overlap the NVLink transfer; chunks stay
         # between 512 MiB and 2 GiB per staging buffer (four buffers)
         chunk = min(half, max(self.CHUNK_MIN, min(half // 4, self.CHUNK_MAX)))
@@ -633,6 +700,9 @@ class ShardedStatevector:
             for req in reqs:
                 req.wait()
             self.engine.unpack_half(vic.li, 1 - B, f0, c0, r0_, factor)
+        self._after_swap(glo, vic, k)
+
+    def _after_swap(self, glo: _Q, vic: _Q, k: int) -> None:
         self.n_swaps += 1
         # the victim's slot now carries `glo` with slot value = physical rank bit; undo a pending relabel
         glo.li, glo.g = vic.li, None

@@ -111,6 +111,7 @@ class B200Statevector:
         self._lib = _lib.load()
         stream, dev = _torch_stream_and_device(device)
         self._device = 0 if dev is None else dev
+        self._stream = stream      # the CUDA stream every kernel of this state is launched on (0 = legacy default)
         self._h = C.c_void_p()
         rc = self._lib.gxsv_create(cap, self._device, C.c_void_p(stream), C.byref(self._h))
         if rc == _lib.GXSV_ENOMEM and fusion == 2 and cap > n and cap >= 30:

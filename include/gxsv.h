@@ -180,6 +180,17 @@ int gxsv_pack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count,
 int gxsv_unpack_half(gxsv_t* h, int q, int bitval, uint64_t first, uint64_t count, const void* in_device,
                      double re, double im);
 
+/* Peer-memory exchange (one process per GPU): every rank exports its register as a CUDA IPC handle (64 bytes), the
+ * host layer all-gathers the handles and each rank opens those of the ranks it pairs with (one slot per rank-index
+ * bit).  gxsv_swap_peer then swaps, IN PLACE on both GPUs through NVLink loads / stores, the half with bit(q) = 1 - my_bit
+ * of this shard with the half with bit(q) = my_bit of the partner's shard (amplitudes arriving here are multiplied by
+ * (fre, fim), those arriving there by its inverse); both partners call it, each handles half of the elements.  The
+ * caller must place a cross-rank barrier on the stream before and after the call ("qubit-remap"). */
+int gxsv_ipc_export(gxsv_t* h, unsigned char handle_out[64]);
+int gxsv_ipc_open(gxsv_t* h, int slot, const unsigned char handle[64]);
+int gxsv_ipc_close(gxsv_t* h);
+int gxsv_swap_peer(gxsv_t* h, int q, int slot, int my_bit, double fre, double fim);
+
 /* ---- density matrices (BASELINE config 5; graphix/sim/density_matrix.py) -------------------------
  * rho over n qubits is held vectorised as a 2n-qubit register: qubit i has a row qubit rows[i] and a
  * column qubit cols[i] (logical indices of this handle).  U rho U^dagger = (U on rows[i], conj(U) on

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-from ref_shim import REFERENCE_ROOT, import_reference  # noqa: E402
+from ref_shim import REFERENCE_ROOT, extract_tests, import_reference  # noqa: E402
 
 import_reference()
 import pytest  # noqa: E402
@@ -56,21 +56,33 @@ def main() -> int:
     from graphix.sim.statevec import Statevector
     from oracle.dm_oracle import OracleDensityMatrix
 
-    DensityMatrix.register(OracleDensityMatrix)
-    graphix.simulator.DensityMatrixBackend = OracleBackedDMBackend
+    if os.environ.get("GXSV_CONFORMANCE_ENGINE") == "cuda":
+        # GPU box: the real CUDA engine under the product backends (tests/test_graphix_dropin_gpu.py)
+        import graphix_b200
 
-    Statevector.register(OracleStatevector)   # same virtual-subclass registration graphix_b200.statevec does for B200Statevector
-    graphix.simulator.StatevectorBackend = OracleBackedBackend
-    graphix.transpiler.StatevectorBackend = OracleBackedBackend
+        graphix.simulator.StatevectorBackend = graphix_b200.B200StatevectorBackend
+        graphix.transpiler.StatevectorBackend = graphix_b200.B200StatevectorBackend
+        graphix.simulator.DensityMatrixBackend = graphix_b200.B200DensityMatrixBackend
+    else:
+        DensityMatrix.register(OracleDensityMatrix)
+        graphix.simulator.DensityMatrixBackend = OracleBackedDMBackend
+        Statevector.register(OracleStatevector)   # same virtual-subclass registration graphix_b200.statevec does for B200Statevector
+        graphix.simulator.StatevectorBackend = OracleBackedBackend
+        graphix.transpiler.StatevectorBackend = OracleBackedBackend
     files = [a for a in sys.argv[1:] if not a.startswith("-")] or ["test_pattern.py", "test_simulator.py",
                                                                    "test_branch_selector.py", "test_transpiler.py",
                                                                    "test_noisy_density_matrix.py", "test_noise_model.py"]
     extra = [a for a in sys.argv[1:] if a.startswith("-")]
     # tensor-network tests cannot run here (quimb is a stub in this container) and are not on the path
-    args = ["-p", "no:cacheprovider", "-o", "addopts=", "-c", "/dev/null", f"--rootdir={REFERENCE_ROOT}", "-q",
-            "-W", "ignore", "-k", "not tensornetwork and not _tn and not mps",
-            *[os.path.join(REFERENCE_ROOT, "tests", f) for f in files], *extra]
-    return pytest.main(args)
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        tests_dir = extract_tests(tmp)        # real files: the reference tree itself, or extracted from the staged archive
+        rootdir = os.path.dirname(tests_dir)
+        args = ["-p", "no:cacheprovider", "-o", "addopts=", "-c", "/dev/null", f"--rootdir={rootdir}", "-q",
+                "-W", "ignore", "-k", "not tensornetwork and not _tn and not mps",
+                *[os.path.join(tests_dir, f) for f in files], *extra]
+        return pytest.main(args)
 
 
 if __name__ == "__main__":

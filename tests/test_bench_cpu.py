@@ -20,9 +20,19 @@ def test_reference_arm_statevector_json_contract():
     d = _run("--workload", "rand11x6", "--steps", "2", "--warmup", "1", "--cpu-window", "40")
     assert d["impl"] == "reference" and d["metric"] == "pattern_sim_commands_per_s" and d["unit"] == "commands/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the real reference (graphix numba backend) when importable here, else the C port
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "commands/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["config"]["workload"] == "rand11x6"
+
+
+def test_reference_arm_port_and_real_reference_agree_on_kind_labels():
+    port = _run("--workload", "rand11x6", "--steps", "1", "--warmup", "0", "--cpu-window", "40", "--port")
+    assert port["cpu_baseline"]["kind"] == "port"
+    if os.path.isdir("/root/reference/graphix") or os.path.exists(os.path.join(ROOT, "oracle", "_ref", "graphix_ref.zip")):
+        real = _run("--workload", "rand11x6", "--steps", "1", "--warmup", "0", "--cpu-window", "40")
+        assert real["cpu_baseline"]["kind"] == "reference" and "numba" in real["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_density_matrix():
