@@ -73,6 +73,7 @@ SIGNATURES = {
     "gxsv_ipc_open": (C.c_int, [_H, C.c_int, C.c_char_p]),
     "gxsv_ipc_close": (C.c_int, [_H]),
     "gxsv_swap_peer": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "gxsv_flush_batch": (C.c_int, [_H]),
     "gxsv_pack_half": (C.c_int, [_H, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
     "gxsv_unpack_half": (C.c_int, [_H, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_double, C.c_double]),
 }

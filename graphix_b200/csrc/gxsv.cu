@@ -1810,15 +1810,20 @@ int gxsv_ipc_close(gxsv_t* h) {
   return GXSV_OK;
 }
 
+int gxsv_flush_batch(gxsv_t* h) {
+  CU(cudaSetDevice(h->device));
+  return flush_batch(h);
+}
+
 int gxsv_swap_peer(gxsv_t* h, int q, int slot, int my_bit, double fre, double fim) {
   CU(cudaSetDevice(h->device));
   int rc = check_q(h, q);
   if (rc) return rc;
+  if (h->batch.nstages)
+    return fail(h, GXSV_EVALUE, "swap_peer: queued projections must be launched (gxsv_flush_batch) before the barrier that precedes the swap");
   if (slot < 0 || slot >= 8 || !h->peer_psi[slot]) return fail(h, GXSV_EVALUE, "swap_peer: no peer register in slot %d", slot);
   if (h->exported_psi != h->psi) return fail(h, GXSV_EVALUE, "swap_peer: the register moved since it was exported");
   if (h->q[q].phys < 0 || has_edge(h, h->q[q].id)) return fail(h, GXSV_EVALUE, "swap_peer: qubit %d must be settled first", q);
-  rc = flush_batch(h);
-  if (rc) return rc;
   const int p = h->q[q].phys;
   const uint64_t half = 1ull << (nlive_bits(h) - 1);
   const int B = my_bit ? 1 : 0;
@@ -1829,10 +1834,24 @@ int gxsv_swap_peer(gxsv_t* h, int q, int slot, int my_bit, double fre, double fi
   const uint64_t my_or = (uint64_t)(1 - B) << p, peer_or = (uint64_t)B << p;
   const cplx f(fre, fim), finv = cplx(1.0) / f;
   const int scale = (f != cplx(1.0, 0.0)) ? 1 : 0;
+  // diagnostics (tools/microbench_swap.py): GXSV_SWAP_MODE = 1 pull only / 2 push only, GXSV_SWAP_U = loads in flight per
+  // thread, GXSV_SWAP_CTAS = CTAs per SM
+  static const int dbg_mode = std::getenv("GXSV_SWAP_MODE") ? std::atoi(std::getenv("GXSV_SWAP_MODE")) : 0;
+  static const int dbg_u = std::getenv("GXSV_SWAP_U") ? std::atoi(std::getenv("GXSV_SWAP_U")) : U_DEF;
+  static const int dbg_ctas = std::getenv("GXSV_SWAP_CTAS") ? std::atoi(std::getenv("GXSV_SWAP_CTAS")) : 8;
   {
     Launch L(h, GXSV_K_MISC, 64.0 * (double)count);
-    k_swap_peer<U_DEF><<<grid_for(h, count, U_DEF), TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or,
-                                                                       first, count, d2(f), d2(finv), scale);
+    const int u = (dbg_u == 8 || dbg_u == 2 || dbg_u == 1) ? dbg_u : U_DEF;
+    uint64_t blocks = (count + (uint64_t)TPB * u - 1) / ((uint64_t)TPB * u);
+    blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)h->sm_count * std::max(1, dbg_ctas)));
+    if (u == 8)
+      k_swap_peer<8><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode);
+    else if (u == 2)
+      k_swap_peer<2><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode);
+    else if (u == 1)
+      k_swap_peer<1><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode);
+    else
+      k_swap_peer<U_DEF><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode);
   }
   return check_launch(h, "k_swap_peer");
 }

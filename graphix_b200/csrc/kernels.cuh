@@ -1138,7 +1138,9 @@ template <int U>
 __global__ void __launch_bounds__(TPB) k_swap_peer(double2* __restrict__ mine, double2* __restrict__ peer,
                                                    const __grid_constant__ Holes hs, const uint64_t my_or,
                                                    const uint64_t peer_or, const uint64_t first, const uint64_t count,
-                                                   const double2 f_mine, const double2 f_peer, const int scale) {
+                                                   const double2 f_mine, const double2 f_peer, const int scale,
+                                                   const int mode) {
+  // mode 0 = swap; 1 / 2 = diagnostics only (tools/microbench_swap.py): pull (mine <- peer) / push (peer <- mine)
   const uint64_t chunk = (uint64_t)TPB * U;
   for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < count; base += (uint64_t)gridDim.x * chunk) {
     double2 a[U], b[U];
@@ -1148,16 +1150,16 @@ __global__ void __launch_bounds__(TPB) k_swap_peer(double2* __restrict__ mine, d
       const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
       e[u] = expand(first + k, hs);
       if (k < count) {
-        b[u] = ld_amp(peer + (e[u] | peer_or));      // NVLink load
-        a[u] = ld_amp(mine + (e[u] | my_or));
+        if (mode != 2) b[u] = ld_amp(peer + (e[u] | peer_or));      // NVLink load
+        if (mode != 1) a[u] = ld_amp(mine + (e[u] | my_or));
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
       if (k < count) {
-        st_amp(peer + (e[u] | peer_or), scale ? cmul(f_peer, a[u]) : a[u]);   // NVLink store
-        st_amp(mine + (e[u] | my_or), scale ? cmul(f_mine, b[u]) : b[u]);
+        if (mode != 1) st_amp(peer + (e[u] | peer_or), scale ? cmul(f_peer, a[u]) : a[u]);   // NVLink store
+        if (mode != 2) st_amp(mine + (e[u] | my_or), scale ? cmul(f_mine, b[u]) : b[u]);
       }
     }
   }

@@ -147,6 +147,9 @@ class GpuShardEngine:
     def stream_handle(self) -> int:
         return self.sv._stream
 
+    def flush_batch(self) -> None:
+        self.sv._check(self._lib.gxsv_flush_batch(self._h))
+
     def norm2_local(self) -> float:
         return self.sv.norm2()
 
@@ -667,6 +670,7 @@ class ShardedStatevector:
             # in-place swap kernels are done before anyone goes on
             if torch.cuda.current_stream().cuda_stream != self.engine.stream_handle():
                 raise RuntimeError("sharded exchange: the current torch stream is not the engine's stream")
+            self.engine.flush_batch()      # queued projections touch the halves the partner is about to read
             self._stream_barrier()
             self.engine.swap_peer(vic.li, k, B, factor)
             self._stream_barrier()

@@ -190,6 +190,9 @@ int gxsv_ipc_export(gxsv_t* h, unsigned char handle_out[64]);
 int gxsv_ipc_open(gxsv_t* h, int slot, const unsigned char handle[64]);
 int gxsv_ipc_close(gxsv_t* h);
 int gxsv_swap_peer(gxsv_t* h, int q, int slot, int my_bit, double fre, double fim);
+/* launch the queued batched projections now (everything this shard still has to do to its register must be on the
+ * stream BEFORE the barrier that precedes a peer swap: the partner reads this register right after that barrier) */
+int gxsv_flush_batch(gxsv_t* h);
 
 /* ---- density matrices (BASELINE config 5; graphix/sim/density_matrix.py) -------------------------
  * rho over n qubits is held vectorised as a 2n-qubit register: qubit i has a row qubit rows[i] and a

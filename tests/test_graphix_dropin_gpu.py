@@ -64,5 +64,5 @@ def test_reference_test_files_pass_on_the_cuda_engine():
     tail = out.stdout[-2500:]
     m = re.search(r"(\d+) passed", out.stdout)
     assert m, (tail, out.stderr[-2000:])
-    assert int(m.group(1)) >= 300, tail
+    assert int(m.group(1)) >= 1000, tail
     assert "failed" not in out.stdout.splitlines()[-1], tail
