@@ -53,6 +53,7 @@ struct ProfRec {
 // the global phase of the result depends on that choice.  It is guessed when the projection is issued
 // (`assumed`) and corrected when the norm is finally known (`ratio` = |row0|^2 / |row1|^2, `phi` = the unit phase).
 struct StageNote {
+  double an = 0.0;       // > 0: the norm^2 after this stage is an * (norm^2 before it), known without looking (Stage::acc = 0)
   double ratio = 0.0;
   cplx phi = 1.0;
   bool big1 = false;
@@ -94,6 +95,7 @@ struct gxsv {
   int profile = 0;
   int batch_axes = MAX_BATCH_AXES;   // distinct physical bits per batched pass (GXSV_BATCH_AXES)
   int chunk_log2 = DEFAULT_CHUNK_LOG2;
+  int analytic_norms = 1;  // skip the norm accumulation of stages whose outcome probability is known to be 1/2
   int use_tma = 0;         // 1: batched passes stage CTA tiles through shared memory with bulk copies (k_fused_tma; measured slower for many
                            // stages per pass, see kernels.cuh) when the layout allows
   int batch_max = 0;       // > 0: queue up to this many fused projections and run them in one pass (non-strict only)
@@ -412,6 +414,8 @@ int flush_batch(gxsv_t* h) {
   Batch bt = h->batch;
   h->batch.nstages = 0;
   h->batch.naxes = 0;
+  bt.st[bt.nstages - 1].acc = 1;             // the last norm of a pass is always measured: it sets the normalisation
+  h->open_notes[bt.nstages - 1].an = 0.0;
   Holes hs;
   hs.n = 0;
   for (int b = 0; b < h->phys_bits; ++b) {
@@ -506,8 +510,9 @@ int check_deferred(gxsv_t* h) {
     if (rc) return rc;
     double prev = 1.0;
     for (int k = 0; k < d.second; ++k) {
-      const double p = v[k] / prev;   // norm^2 of the kept (larger) row for a normalised input
       const StageNote& nt = d.note[k];
+      if (nt.an > 0.0) v[k] = prev * nt.an;      // not accumulated: known analytically
+      const double p = v[k] / prev;   // norm^2 of the kept (larger) row for a normalised input
       const double n0 = nt.big1 ? p * nt.ratio : p, n1 = nt.big1 ? p : p * nt.ratio;
       if (!(n0 > 1e-10) && !(n1 > 1e-10))
         return fail(h, GXSV_EZERONORM, "Attempted to remove a qubit from 0-norm statevector (detected at sync).");
@@ -858,6 +863,7 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
     if (v >= 1 && v <= MAX_TILE_AXES) h->batch_axes = v;
   }
   if (const char* tm = std::getenv("GXSV_TMA")) h->use_tma = std::atoi(tm) ? 1 : 0;
+  if (const char* an = std::getenv("GXSV_ANALYTIC_NORMS")) h->analytic_norms = std::atoi(an) ? 1 : 0;
   if (const char* cl = std::getenv("GXSV_CHUNK_LOG2")) {
     const int v = std::atoi(cl);
     if (v >= 0 && v <= 10) h->chunk_log2 = v;
@@ -1400,10 +1406,20 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           }
           const int k = h->batch.nstages - 1;
           h->batch.nscale[k] = ((k > 0 && !h->dist) ? h->batch.nscale[k - 1] : 1.0) * std::norm(f);
+          // |a| = 1 (XY-plane measurement, |+> / |-> partner): the outcome probability is 1/2 whatever the state, i.e.
+          // |row . psi|^2 = 2 |s0|^2 |row_pivot|^2 |psi|^2 — no need to accumulate the norm of this stage
+          st.acc = 1;
+          double an = 0.0;
+          if (fast && std::abs(std::norm(cplx(st.a.x, st.a.y)) - 1.0) <= 1e-12 && h->analytic_norms) {
+            const cplx mp = big ? (pivot ? m11 : m10) : (pivot ? m01 : m00);
+            an = 2.0 * std::norm(s0) * std::norm(mp);
+            st.acc = 0;
+          }
           h->q[vi].phys = p;
           h->q.erase(h->q.begin() + q);
           h->hscale = fast ? (h->dist ? f : f / std::abs(f)) : cplx(1.0);
           h->open_notes[h->batch.nstages - 1] = phase_note(h, big, r0, r1, m00, m01, m10, m11);
+          h->open_notes[h->batch.nstages - 1].an = an;
           if (!h->deferred.empty() && h->seq - h->deferred.front().first > (unsigned long long)(RING - 64)) {
             rc = check_deferred(h);   // never let the ring wrap over a result that has not been checked
             if (rc) return rc;
@@ -1718,7 +1734,8 @@ int gxsv_take_norms(gxsv_t* h, double* out, int cap, int* count) {
     if (rc) return rc;
     for (int k = 0; k < d.second; ++k) {
       if (n >= cap) return fail(h, GXSV_EVALUE, "take_norms: more than %d results pending", cap);
-      out[n++] = v[k];
+      // a stage whose norm was not accumulated reports MINUS its analytic ratio (norm after / norm before)
+      out[n++] = (d.note[k].an > 0.0) ? -d.note[k].an : v[k];
     }
   }
   h->deferred.clear();

@@ -403,7 +403,8 @@ struct Stage {
   int axis;                      // batch axis index
   unsigned char kind;            // 0 / 1 / 2, see above
   unsigned char neg;             // kinds 0/1: s1 = -s0
-  unsigned short pad;
+  unsigned char acc;             // 1 = accumulate the norm^2 after this stage (0: the host knows it analytically)
+  unsigned char pad;
   unsigned int qtab, vtab;       // set when the pass is launched (depend on the register assignment of the axes):
                                  // byte k = 0x80 iff the k-th amplitude pair of the stage's axis takes the sign
 };
@@ -419,66 +420,64 @@ __device__ __forceinline__ double flip_sign(const double x, const unsigned int s
   return __hiloint2double(__double2hiint(x) ^ (int)s31, __double2loint(x));
 }
 
+// The 2^(NB-1) amplitude pairs of one stage on register axis AX.  KIND as in Stage; ACC = accumulate the norm^2 of
+// the results (two chains).  For kinds 0 / 1 with |a| = 1 — every XY-plane measurement of a qubit whose partner was
+// prepared in |+> — the norm after the stage is exactly 2 |in|^2 whatever the data (the outcome probability of such a
+// measurement is 1/2), so the host asks for the accumulation only where it cannot know the answer (Stage::acc).
+template <int NB, int AX, int KIND, bool ACC>
+__device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& st, const unsigned int tq,
+                                            const unsigned int tv, double& nrm0, double& nrm1) {
+  const double2 a = st.a;
+#pragma unroll
+  for (int lo = 0; lo < (1 << NB); ++lo) {
+    if ((lo >> AX) & 1) continue;
+    const int hi = lo | (1 << AX);
+    const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded at compile time)
+    const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | (k << 12)), sv = __byte_perm(tv, 0u, 0x0444 | (k << 12));
+    double2 r0, r1;
+    if (KIND == 0) {
+      double2 w = cmul(a, v[hi]);
+      w.x = flip_sign(w.x, sq);
+      w.y = flip_sign(w.y, sq);
+      r0 = make_double2(v[lo].x + w.x, v[lo].y + w.y);
+      r1 = make_double2(flip_sign(v[lo].x - w.x, sv), flip_sign(v[lo].y - w.y, sv));
+    } else if (KIND == 1) {
+      const double2 u = cmul(a, v[lo]);
+      const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
+      r0 = make_double2(u.x + t1.x, u.y + t1.y);
+      r1 = make_double2(flip_sign(u.x - t1.x, sv), flip_sign(u.y - t1.y, sv));
+    } else {
+      const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
+      r0 = cmad2(st.m00, v[lo], st.m01, t1);
+      r1 = cmad2(st.m10, v[lo], st.m11, t1);
+      r1.x = flip_sign(r1.x, sv);
+      r1.y = flip_sign(r1.y, sv);
+    }
+    if (ACC) {
+      nrm0 = fma(r0.x, r0.x, nrm0); nrm1 = fma(r0.y, r0.y, nrm1);
+      nrm0 = fma(r1.x, r1.x, nrm0); nrm1 = fma(r1.y, r1.y, nrm1);
+    }
+    v[lo] = r0;
+    v[hi] = r1;
+  }
+}
+
 // Apply stage `st` on register axis AX of the 2^NB amplitudes a thread holds; gpar_q / gpar_v = parity of the thread's
-// fixed physical index bits in st.mq / st.mv.  Adds the norm^2 of the 2^NB results to nrm0 / nrm1 (two chains).
+// fixed physical index bits in st.mq / st.mv.  Adds the norm^2 of the 2^NB results to nrm0 / nrm1 when st.acc is set.
 template <int NB, int AX>
 __device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage& st, const unsigned int gpar_q,
                                               const unsigned int gpar_v, double& nrm0, double& nrm1) {
   // byte k of tq / tv = 0x80 iff the k-th amplitude pair takes the sign
   const unsigned int tq = st.qtab ^ ((gpar_q & 1u) ? 0x80808080u : 0u);
   const unsigned int tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x80808080u : 0u);
-  const double2 a = st.a;
   if (st.kind == 0) {
-#pragma unroll
-    for (int lo = 0; lo < (1 << NB); ++lo) {
-      if ((lo >> AX) & 1) continue;
-      const int hi = lo | (1 << AX);
-      const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded)
-      const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | (k << 12)), sv = __byte_perm(tv, 0u, 0x0444 | (k << 12));
-      double2 w = cmul(a, v[hi]);
-      w.x = flip_sign(w.x, sq);
-      w.y = flip_sign(w.y, sq);
-      const double2 r0 = make_double2(v[lo].x + w.x, v[lo].y + w.y);
-      const double2 r1 = make_double2(flip_sign(v[lo].x - w.x, sv), flip_sign(v[lo].y - w.y, sv));
-      nrm0 = fma(r0.x, r0.x, nrm0); nrm1 = fma(r0.y, r0.y, nrm1);
-      nrm0 = fma(r1.x, r1.x, nrm0); nrm1 = fma(r1.y, r1.y, nrm1);
-      v[lo] = r0;
-      v[hi] = r1;
-    }
+    if (st.acc) stage_pairs<NB, AX, 0, true>(v, st, tq, tv, nrm0, nrm1);
+    else stage_pairs<NB, AX, 0, false>(v, st, tq, tv, nrm0, nrm1);
   } else if (st.kind == 1) {
-#pragma unroll
-    for (int lo = 0; lo < (1 << NB); ++lo) {
-      if ((lo >> AX) & 1) continue;
-      const int hi = lo | (1 << AX);
-      const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded)
-      const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | (k << 12)), sv = __byte_perm(tv, 0u, 0x0444 | (k << 12));
-      const double2 u = cmul(a, v[lo]);
-      const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
-      const double2 r0 = make_double2(u.x + t1.x, u.y + t1.y);
-      const double2 r1 = make_double2(flip_sign(u.x - t1.x, sv), flip_sign(u.y - t1.y, sv));
-      nrm0 = fma(r0.x, r0.x, nrm0); nrm1 = fma(r0.y, r0.y, nrm1);
-      nrm0 = fma(r1.x, r1.x, nrm0); nrm1 = fma(r1.y, r1.y, nrm1);
-      v[lo] = r0;
-      v[hi] = r1;
-    }
+    if (st.acc) stage_pairs<NB, AX, 1, true>(v, st, tq, tv, nrm0, nrm1);
+    else stage_pairs<NB, AX, 1, false>(v, st, tq, tv, nrm0, nrm1);
   } else {
-    const double2 m00 = st.m00, m01 = st.m01, m10 = st.m10, m11 = st.m11;
-#pragma unroll
-    for (int lo = 0; lo < (1 << NB); ++lo) {
-      if ((lo >> AX) & 1) continue;
-      const int hi = lo | (1 << AX);
-      const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded)
-      const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | (k << 12)), sv = __byte_perm(tv, 0u, 0x0444 | (k << 12));
-      const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
-      const double2 r0 = cmad2(m00, v[lo], m01, t1);
-      double2 r1 = cmad2(m10, v[lo], m11, t1);
-      r1.x = flip_sign(r1.x, sv);
-      r1.y = flip_sign(r1.y, sv);
-      nrm0 = fma(r0.x, r0.x, nrm0); nrm1 = fma(r0.y, r0.y, nrm1);
-      nrm0 = fma(r1.x, r1.x, nrm0); nrm1 = fma(r1.y, r1.y, nrm1);
-      v[lo] = r0;
-      v[hi] = r1;
-    }
+    stage_pairs<NB, AX, 2, true>(v, st, tq, tv, nrm0, nrm1);
   }
 }
 
@@ -526,7 +525,7 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_batch(double2* __restrict__ ps
       if (la == 0) stage_on_axis<A, 0>(v, st, pq, pv, n0, n1);
       if (A > 1 && la == 1) stage_on_axis<A, (A > 1 ? 1 : 0)>(v, st, pq, pv, n0, n1);
       if (A > 2 && la == 2) stage_on_axis<A, (A > 2 ? 2 : 0)>(v, st, pq, pv, n0, n1);
-      sacc[s][threadIdx.x] += n0 + n1;
+      if (st.acc) sacc[s][threadIdx.x] += n0 + n1;
     }
 #pragma unroll
     for (int b = 0; b < D; ++b) st_amp(psi + base + off_of(b), v[b]);
@@ -623,7 +622,7 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi
           if (la == 0) stage_on_axis<3, 0>(v, st, pq, pv, n0, n1);
           else if (la == 1) stage_on_axis<3, 1>(v, st, pq, pv, n0, n1);
           else stage_on_axis<3, 2>(v, st, pq, pv, n0, n1);
-          sacc[s][tid] += n0 + n1;
+          if (st.acc) sacc[s][tid] += n0 + n1;
         }
         if (p + 1 < nphases) {
           // transpose through the warp's private tile to the register assignment of the next phase
@@ -783,7 +782,7 @@ __global__ void __launch_bounds__(TPB, 2) k_fused_tma(double2* __restrict__ psi,
         if (la == 0) stage_on_axis<3, 0>(v, st, pq, pv, n0, n1);
         else if (la == 1) stage_on_axis<3, 1>(v, st, pq, pv, n0, n1);
         else stage_on_axis<3, 2>(v, st, pq, pv, n0, n1);
-        sacc[s][tid] += n0 + n1;
+        if (st.acc) sacc[s][tid] += n0 + n1;
       }
 #pragma unroll
       for (int bb = 0; bb < 8; ++bb) tb[soff(bb)] = v[bb];

@@ -861,9 +861,13 @@ class ShardedStatevector:
         window, self._window = self._window, []
         if len(local) != len(window):
             raise RuntimeError(f"sharded state: {len(local)} norms for {len(window)} projections")
-        tot = self._allreduce([rec[0] * n for rec, n in zip(window, local, strict=True)])
+        # a negative entry is MINUS the analytic ratio (norm after / norm before) of a projection whose norm the engine did
+        # not accumulate (outcome probability known to be 1/2, see gxsv_take_norms); the same on every rank
+        tot = self._allreduce([rec[0] * n if n >= 0 else 0.0 for rec, n in zip(window, local, strict=True)])
         prev = 1.0                       # the window starts from a normalised state (g was set by the last _renorm)
-        for (_, big, ratio, phi, assumed, qubit), n in zip(window, tot, strict=True):
+        for i, ((_, big, ratio, phi, assumed, qubit), n) in enumerate(zip(window, tot, strict=True)):
+            if local[i] < 0:
+                n = tot[i] = prev * (-local[i])
             p = n / prev                 # norm^2 of the kept (larger) row for a normalised input
             n0, n1 = (p * ratio, p) if big else (p, p * ratio)
             if not n0 > 1e-10 and not n1 > 1e-10:

@@ -253,6 +253,16 @@ class B200Statevector:
         """statevec.py:222-229 (a host copy here, not a view)."""
         return self.flatten()
 
+    @property
+    def _psi(self) -> np.ndarray:
+        """Host buffer of ``2**max_qubits`` amplitudes whose first ``2**nqubit`` entries are the state — what the
+        reference's own copy constructor reads from a ``Statevector`` instance (``Statevector(other)``,
+        statevec.py:128-135, used e.g. by ``DensityMatrix(statevec)``); this class is registered as a virtual
+        ``Statevector`` subclass, so graphix code may take that path.  A copy, made on demand."""
+        buf = np.empty(1 << self.max_qubits, dtype=np.complex128)
+        self.flatten(out=buf[: 1 << self.nqubit])
+        return buf
+
     def add_nodes(self, nqubit: int, data) -> None:
         """statevec.py:269-300."""
         if nqubit == 1 and data is BasicStates.PLUS:
