@@ -54,6 +54,9 @@ SIGNATURES = {
     "gxsv_flatten": (C.c_int, [_H, C.c_void_p]),
     "gxsv_flatten_device": (C.c_int, [_H, C.c_void_p]),
     "gxsv_fidelity": (C.c_int, [_H, _H, _D]),
+    "gxsv_inner": (C.c_int, [_H, _H, _D]),
+    "gxsv_clone": (C.c_int, [_H, C.POINTER(_H)]),
+    "gxsv_nonzero": (C.c_int, [_H, C.c_double, C.c_uint64, C.POINTER(C.c_uint64), _D, C.POINTER(C.c_uint64)]),
     "gxsv_norm2": (C.c_int, [_H, _D]),
     "gxsv_set_state": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "gxsv_sync": (C.c_int, [_H]),

@@ -889,6 +889,14 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
 int gxsv_create_external(void* device_buffer, int cap_qubits, int device, void* stream, gxsv_t** out) {
   gxsv_t* h = nullptr;
   if (!out || !device_buffer) return fail(h, GXSV_EVALUE, "NULL argument");
+  if (cap_qubits < 0 || cap_qubits > 40) return fail(h, GXSV_EVALUE, "`cap_qubits` must be in [0, 40], got %d", cap_qubits);
+  {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      return fail(h, GXSV_ECUDA, "no CUDA device available (%s): the gxsv engine has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(h, GXSV_EVALUE, "device %d out of range [0, %d)", device, ndev);
+  }
   h = new gxsv();
   h->device = device;
   h->stream = (cudaStream_t)stream;
@@ -1104,7 +1112,12 @@ int gxsv_entangle(gxsv_t* h, int q1, int q2) {
   if (rc) return rc;
   rc = check_q(h, q2);
   if (rc) return rc;
-  if (q1 == q2) return fail(h, GXSV_EVALUE, "entangle: control and target must differ");
+  if (q1 == q2) {
+    // the reference's kernel flips every amplitude whose bits of q1 AND q2 are set (statevec.py:930-937): for equal
+    // indices that is Z on the qubit
+    const double z[8] = {1.0, 0.0, 0.0, 0.0, 0.0, 0.0, -1.0, 0.0};
+    return gxsv_evolve_single(h, q1, z);
+  }
   h->pend.push_back({h->q[q1].id, h->q[q2].id});
   if (h->fusion == 0) { CU(cudaSetDevice(h->device)); return flush_pending(h); }
   return GXSV_OK;
@@ -1250,6 +1263,16 @@ int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) 
         const int big = (r0 >= r1) ? 0 : 1;
         const double nb = std::sqrt(big ? r1 : r0);
         const cplx c0 = (big ? m10 : m00) / nb, c1 = (big ? m11 : m01) / nb;   // the bra <v| up to a phase
+        if (!h->dist && h->analytic_norms && std::abs(w_even - w_odd) <= 1e-15 &&
+            std::abs(std::norm(c0) - std::norm(c1)) <= 1e-14) {
+          // one of the queued CZ partners is a not-yet-materialised qubit with |s0|^2 = |s1|^2 (every |+> of an (N, E, M)
+          // stream) and the measurement is in the XY plane: p = 1/2 (|t0|^2 + |t1|^2 summed) = |c0|^2 N0 + |c1|^2 N1 = 1/2
+          // for ANY normalised state — no pass over the register, and no flush of the queued projections
+          out[0] = 0.5;
+          out[1] = 0.0;
+          h->stats.launches[GXSV_K_EXPECT] += 0;
+          return GXSV_OK;
+        }
         const int p = h->q[q].phys;
         const uint64_t npair = 1ull << (nlive_bits(h) - 1);
         Holes hs = make_holes(h, p);
@@ -1602,34 +1625,113 @@ int gxsv_norm2(gxsv_t* h, double* out) {
   return GXSV_OK;
 }
 
-int gxsv_fidelity(gxsv_t* a, gxsv_t* b, double* out) {
+// <a|b> with both registers read in place through their gather tables (no canonical copies, so it works up to the
+// full capacity of the device).  out[0..1] = (re, im) of the TRUE inner product (pending scalars applied).
+static int inner_in_place(gxsv_t* a, gxsv_t* b, double out[2]) {
   gxsv_t* h = a;
   if (a->q.size() != b->q.size()) return fail(h, GXSV_EVALUE, "fidelity: qubit counts differ (%d vs %d)", (int)a->q.size(), (int)b->q.size());
   if (a->device != b->device) return fail(h, GXSV_EVALUE, "fidelity: states live on different devices");
   CU(cudaSetDevice(a->device));
-  const uint64_t total = 1ull << a->q.size();
-  double2 *xa = nullptr, *xb = nullptr;
-  CU(cudaMalloc(&xa, sizeof(double2) * total));
-  cudaError_t e = cudaMalloc(&xb, sizeof(double2) * total);
-  if (e != cudaSuccess) { cudaFree(xa); return fail(h, GXSV_ENOMEM, "fidelity: no room for canonical copies"); }
-  int rc = gxsv_flatten_device(a, xa);
-  if (!rc) rc = gxsv_flatten_device(b, xb);
-  if (!rc) {
-    cudaStreamSynchronize(b->stream);
-    unsigned long long seq;
-    Res* slot = next_slot(a, &seq);
-    {
-      Launch L(a, GXSV_K_EXPECT, 32.0 * (double)total);
-      k_inner<U_DEF><<<grid_for(a, total, U_DEF), TPB, 0, a->stream>>>(xa, xb, total, a->partials, a->ctrl, slot, seq);
-    }
-    rc = check_launch(a, "k_inner");
-    double v[8];
-    if (!rc) rc = wait_slot(a, seq, v);
-    if (!rc) *out = v[0] * v[0] + v[1] * v[1];
+  for (gxsv_t* s : {a, b}) {
+    int rc = check_deferred(s);
+    if (!rc) rc = flush_pending(s);
+    if (!rc) rc = upload_tables(s);
+    if (rc) { if (s != h) h->err = s->err; return rc; }
   }
-  cudaStreamSynchronize(a->stream);
-  cudaFree(xa);
-  cudaFree(xb);
+  cudaStreamSynchronize(b->stream);
+  Ctrl ca, cb;
+  CU(cudaMemcpyAsync(&ca, a->ctrl, sizeof ca, cudaMemcpyDeviceToHost, a->stream));
+  CU(cudaMemcpyAsync(&cb, b->ctrl, sizeof cb, cudaMemcpyDeviceToHost, a->stream));
+  CU(cudaStreamSynchronize(a->stream));
+  const uint64_t total = 1ull << a->q.size();
+  unsigned long long seq;
+  Res* slot = next_slot(a, &seq);
+  {
+    Launch L(a, GXSV_K_EXPECT, 32.0 * (double)total);
+    k_inner_gather<<<grid_for(a, total, 4), TPB, 0, a->stream>>>(a->psi, a->tabs_dev, b->psi, b->tabs_dev, total,
+                                                                   a->partials, a->ctrl, slot, seq);
+  }
+  int rc = check_launch(a, "k_inner_gather");
+  if (rc) return rc;
+  double v[8];
+  rc = wait_slot(a, seq, v);
+  if (rc) return rc;
+  const cplx z = cplx(v[0], v[1]) * std::conj(a->hscale * ca.g) * (b->hscale * cb.g);
+  out[0] = z.real();
+  out[1] = z.imag();
+  return GXSV_OK;
+}
+
+int gxsv_inner(gxsv_t* a, gxsv_t* b, double out[2]) { return inner_in_place(a, b, out); }
+
+int gxsv_fidelity(gxsv_t* a, gxsv_t* b, double* out) {
+  double z[2];
+  int rc = inner_in_place(a, b, z);
+  if (rc) return rc;
+  *out = z[0] * z[0] + z[1] * z[1];
+  return GXSV_OK;
+}
+
+// A second register holding a copy of the state (same layout, same pending work applied first).
+int gxsv_clone(gxsv_t* h, gxsv_t** out) {
+  CU(cudaSetDevice(h->device));
+  int rc = check_deferred(h);
+  if (!rc) rc = flush_pending(h);
+  if (rc) return rc;
+  gxsv_t* c = nullptr;
+  rc = gxsv_create(std::max(h->phys_bits, (int)h->q.size()), h->device, (void*)h->stream, &c);
+  if (rc) { h->err = g_err; return rc; }
+  c->fusion = h->fusion;
+  c->q = h->q;
+  c->next_id = h->next_id;
+  c->phys_bits = h->phys_bits;
+  c->live_mask = h->live_mask;
+  c->hscale = h->hscale;
+  cudaError_t e = cudaMemcpyAsync(c->psi, h->psi, sizeof(double2) << h->phys_bits, cudaMemcpyDeviceToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { gxsv_destroy(c); return fail(h, GXSV_ECUDA, "clone: %s", cudaGetErrorString(e)); }
+  *out = c;
+  return GXSV_OK;
+}
+
+// Sparse read-out: entries with |amp| > atol in canonical order are NOT sorted (the host sorts by index).
+int gxsv_nonzero(gxsv_t* h, double atol, unsigned long long cap, unsigned long long* idx_host, double* amp_host,
+                 unsigned long long* count) {
+  CU(cudaSetDevice(h->device));
+  int rc = check_deferred(h);
+  if (!rc) rc = flush_pending(h);
+  if (!rc) rc = upload_tables(h);
+  if (rc) return rc;
+  unsigned long long *dcount = nullptr, *didx = nullptr;
+  double2* damp = nullptr;
+  CU(cudaMalloc(&dcount, sizeof(unsigned long long)));
+  cudaError_t e = cudaMalloc(&didx, sizeof(unsigned long long) * std::max<unsigned long long>(cap, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&damp, sizeof(double2) * std::max<unsigned long long>(cap, 1));
+  if (e != cudaSuccess) { cudaGetLastError(); cudaFree(dcount); cudaFree(didx); return fail(h, GXSV_ENOMEM, "nonzero: no room for %llu entries", cap); }
+  cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), h->stream);
+  const uint64_t total = 1ull << h->q.size();
+  {
+    Launch L(h, GXSV_K_GATHER, 16.0 * (double)total);
+    k_nonzero<<<grid_for(h, total, 4), TPB, 0, h->stream>>>(h->psi, h->tabs_dev, total, d2(h->hscale), h->ctrl, atol, dcount,
+                                                             didx, damp, cap);
+  }
+  rc = check_launch(h, "k_nonzero");
+  unsigned long long n = 0;
+  if (!rc) {
+    cudaMemcpyAsync(&n, dcount, sizeof n, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    *count = n;
+    const unsigned long long m = std::min(n, cap);
+    if (m) {
+      cudaMemcpyAsync(idx_host, didx, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost, h->stream);
+      cudaMemcpyAsync(amp_host, damp, sizeof(double2) * m, cudaMemcpyDeviceToHost, h->stream);
+      cudaStreamSynchronize(h->stream);
+    }
+  }
+  cudaFree(dcount);
+  cudaFree(didx);
+  cudaFree(damp);
   return rc;
 }
 

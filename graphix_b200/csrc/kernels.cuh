@@ -137,7 +137,7 @@ __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restric
   if (threadIdx.x == 0) {
     ctrl->ticket = 0;
     if (mode == FIN_CONTRACT) {
-      ctrl->g = 1.0 / sqrt(tot[0]);
+      ctrl->g = tot[0] > 0.0 ? 1.0 / sqrt(tot[0]) : 1.0;
       res->v[0] = tot[0] * (nscale ? nscale[0] : 1.0);
     } else if (mode == FIN_CONTRACT_DIST) {
       res->v[0] = tot[0];
@@ -146,7 +146,9 @@ __device__ __forceinline__ void grid_finish(double (&acc)[NV], double* __restric
       // the unfactored state, g normalises what is stored
 #pragma unroll
       for (int k = 0; k < NV; ++k) res->v[k] = tot[k] * (nscale ? nscale[k] : 1.0);
-      ctrl->g = 1.0 / sqrt(tot[(int)post - 1]);
+      // a zero norm (an impossible branch was taken) keeps g finite: the stored zeros stay zeros instead of NaNs, and the
+      // deferred check raises the reference's RuntimeError as the first error the caller sees
+      ctrl->g = tot[(int)post - 1] > 0.0 ? 1.0 / sqrt(tot[(int)post - 1]) : 1.0;
     } else if (mode == FIN_ONESHOT) {
       // sharded, non-blocking: publish the local norms; the pending factor g has been consumed by this pass and
       // stays 1 until the host sets it again from the all-reduced norm (gxsv_set_norm)
@@ -996,6 +998,59 @@ __global__ void __launch_bounds__(TPB) k_gather(const double2* __restrict__ psi,
     const uint64_t p = st[0][i & 255] | st[1][(i >> 8) & 255] | st[2][(i >> 16) & 255] | st[3][(i >> 24) & 255] |
                        st[4][(i >> 32) & 255];
     out[k] = cmul(f, __ldg(psi + p));
+  }
+}
+
+// <a|b> of two registers in their own physical layouts (no canonical copies): canonical index i is scattered to each
+// layout through that register's byte tables.  -> (re, im), unscaled.
+__global__ void __launch_bounds__(TPB) k_inner_gather(const double2* __restrict__ xa, const GatherTables* __restrict__ ta,
+                                                      const double2* __restrict__ xb, const GatherTables* __restrict__ tb,
+                                                      const uint64_t n, double* __restrict__ partials, Ctrl* ctrl,
+                                                      Res* res, const unsigned long long seq) {
+  __shared__ uint64_t sa[5][256];
+  __shared__ uint64_t sb[5][256];
+  for (int i = threadIdx.x; i < 5 * 256; i += TPB) {
+    sa[i >> 8][i & 255] = ta->t[i >> 8][i & 255];
+    sb[i >> 8][i & 255] = tb->t[i >> 8][i & 255];
+  }
+  __syncthreads();
+  double acc[2] = {0.0, 0.0};
+  for (uint64_t i = (uint64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (uint64_t)gridDim.x * TPB) {
+    const uint64_t pa = sa[0][i & 255] | sa[1][(i >> 8) & 255] | sa[2][(i >> 16) & 255] | sa[3][(i >> 24) & 255] |
+                        sa[4][(i >> 32) & 255];
+    const uint64_t pb = sb[0][i & 255] | sb[1][(i >> 8) & 255] | sb[2][(i >> 16) & 255] | sb[3][(i >> 24) & 255] |
+                        sb[4][(i >> 32) & 255];
+    const double2 a = __ldg(xa + pa), b = __ldg(xb + pb);
+    acc[0] += a.x * b.x + a.y * b.y;
+    acc[1] += a.x * b.y - a.y * b.x;
+  }
+  grid_finish<2>(acc, partials, ctrl, res, seq, FIN_SCALED, 1.0, 1.0);
+}
+
+// Sparse read-out (Statevector.to_dict / to_prob_dict, statevec.py:591-678): canonical indices and amplitudes of the
+// entries with |amp| > atol are appended to (idx, amp) through one atomic counter; at most `cap` are stored, the
+// counter keeps counting so that the host can tell an overflow.
+__global__ void __launch_bounds__(TPB) k_nonzero(const double2* __restrict__ psi, const GatherTables* __restrict__ tabs,
+                                                 const uint64_t count, const double2 h, const Ctrl* ctrl,
+                                                 const double atol, unsigned long long* __restrict__ counter,
+                                                 unsigned long long* __restrict__ idx_out, double2* __restrict__ amp_out,
+                                                 const unsigned long long cap) {
+  __shared__ uint64_t st[5][256];
+  for (int i = threadIdx.x; i < 5 * 256; i += TPB) st[i >> 8][i & 255] = tabs->t[i >> 8][i & 255];
+  __syncthreads();
+  const double g = ctrl->g;
+  const double2 f = make_double2(h.x * g, h.y * g);
+  for (uint64_t i = (uint64_t)blockIdx.x * TPB + threadIdx.x; i < count; i += (uint64_t)gridDim.x * TPB) {
+    const uint64_t p = st[0][i & 255] | st[1][(i >> 8) & 255] | st[2][(i >> 16) & 255] | st[3][(i >> 24) & 255] |
+                       st[4][(i >> 32) & 255];
+    const double2 a = cmul(f, __ldg(psi + p));
+    if (sqrt(cnorm2(a)) > atol) {
+      const unsigned long long slot = atomicAdd(counter, 1ull);
+      if (slot < cap) {
+        idx_out[slot] = i;
+        amp_out[slot] = a;
+      }
+    }
   }
 }
 

@@ -412,7 +412,8 @@ class ShardedStatevector:
     def entangle(self, qubits: tuple[int, int]) -> None:
         a, b = self._check(qubits[0]), self._check(qubits[1])
         if a is b:
-            raise ValueError("entangle: control and target must differ")
+            self.evolve_single(_Z, qubits[0])      # statevec.py:930-937 with equal indices: Z on the qubit
+            return
         if a.g is None and b.g is None:
             self.engine.entangle(a.li, b.li)
         elif a.g is not None and b.g is not None:

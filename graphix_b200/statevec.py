@@ -297,10 +297,20 @@ class B200Statevector:
         self._check(self._lib.gxsv_evolve(self._h, k, q, a.ctypes.data_as(C.c_void_p)))
 
     def expectation_value(self, op, qubits: Sequence[int]) -> complex:
-        """<psi| op |psi> for a k-qubit operator — statevec.py:397-415 (same recipe: evolve a copy, then <psi|.>)."""
-        other = B200Statevector(self, device=self._device)
+        """<psi| op |psi> for a k-qubit operator — statevec.py:397-415 (same recipe: evolve a copy, then <psi|.>), all on
+        the device: the copy is a second register (``gxsv_clone``), the inner product reads both registers in place."""
+        other = self._clone()
         other.evolve(op, qubits)
-        return complex(np.dot(self.flatten().conjugate(), other.flatten()))
+        out = (C.c_double * 2)()
+        self._check(self._lib.gxsv_inner(self._h, other._h, out))
+        return complex(out[0], out[1])
+
+    def _clone(self) -> "B200Statevector":
+        new = object.__new__(B200Statevector)
+        new._lib, new._device, new._stream = self._lib, self._device, self._stream
+        new._h = C.c_void_p()
+        self._check(self._lib.gxsv_clone(self._h, C.byref(new._h)))
+        return new
 
     def remove_qubit(self, qubit: int) -> None:
         """statevec.py:417-428."""
@@ -368,11 +378,29 @@ class B200Statevector:
         return statevec_to_str(self, output, encoding=encoding, max_denominator=max_denominator, atol=atol, rtol=rtol,
                                precision=precision)
 
+    SPARSE_CAP = 1 << 20     # entries a sparse read-out may return before falling back to a full flatten()
+
     def _to_dict_map(self, f, encoding: str, *, rtol: float, atol: float) -> dict:
-        flat = self.flatten()
+        """statevec.py:591-678.  The entries with ``|amp| > atol`` (``np.isclose(|amp|, 0, rtol, atol)`` compares with
+        ``atol + rtol * 0``) are compacted on the device — only they cross to the host, not the 2**n amplitudes."""
+        del rtol
         n = self.nqubit
-        keep = np.flatnonzero(~np.isclose(np.abs(flat), 0, rtol=rtol, atol=atol))
-        vals = f(flat[keep])
+        lib = getattr(self, "_lib", None)
+        keep = vals = None
+        if lib is not None and hasattr(lib, "gxsv_nonzero"):
+            cap = min(1 << n, self.SPARSE_CAP)
+            idx = np.empty(cap, dtype=np.uint64)
+            amp = np.empty(cap, dtype=np.complex128)
+            count = C.c_uint64()
+            self._check(lib.gxsv_nonzero(self._h, float(atol), cap, idx.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                         amp.ctypes.data_as(C.POINTER(C.c_double)), C.byref(count)))
+            if count.value <= cap:
+                order = np.argsort(idx[: count.value], kind="stable")
+                keep, vals = idx[: count.value][order].astype(np.int64), f(amp[: count.value][order])
+        if keep is None:
+            flat = self.flatten()
+            keep = np.flatnonzero(np.abs(flat) > atol)
+            vals = f(flat[keep])
         keys = [format(int(i), f"0{n}b") if n else "0" for i in keep]
         if encoding == "LSB":
             keys = [k[::-1] for k in keys]

@@ -151,8 +151,18 @@ int gxsv_permute(gxsv_t* h, const int* perm, int n);
 int gxsv_flatten(gxsv_t* h, double* out_host);
 /* same, to DEVICE memory owned by the caller (2^nqubit complex128) */
 int gxsv_flatten_device(gxsv_t* h, void* out_device);
-/* |<a|b>|^2 on device — Statevector.fidelity statevec.py:552-568 */
+/* |<a|b>|^2 on device — Statevector.fidelity statevec.py:552-568; both registers are read in place through their
+ * own layouts (no canonical copies) */
 int gxsv_fidelity(gxsv_t* a, gxsv_t* b, double* out);
+/* <a|b> (re, im) — the inner product Statevector.expectation_value ends with (statevec.py:397-415) */
+int gxsv_inner(gxsv_t* a, gxsv_t* b, double out[2]);
+/* a second register holding a copy of the state — the deepcopy of Statevector.expectation_value (statevec.py:411) */
+int gxsv_clone(gxsv_t* h, gxsv_t** out);
+/* sparse read-out for Statevector.to_dict / to_prob_dict (statevec.py:591-678): canonical indices (qubit 0 = MSB) and
+ * amplitudes of the entries with |amp| > atol, in no particular order; *count = how many there are (may exceed cap: then
+ * only cap were stored) */
+int gxsv_nonzero(gxsv_t* h, double atol, unsigned long long cap, unsigned long long* idx_host, double* amp_host,
+                 unsigned long long* count);
 /* <psi|psi> of the live state (1 for a normalized state) */
 int gxsv_norm2(gxsv_t* h, double* out);
 /* replace the state by 2^n host amplitudes in reference order (Statevector(data), statevec.py:93-216) */

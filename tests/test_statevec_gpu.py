@@ -471,3 +471,76 @@ def test_batched_passes_on_many_axes_against_oracle(n, axes, glog, tma):
     passes = dev.stats()["fused"]["launches"] - npass0
     if axes >= 5:
         assert passes <= 16          # 48 stages: at least three per pass on average
+
+
+def test_read_outs_on_the_device():
+    """Sparse to_dict / to_prob_dict (statevec.py:591-678) compacted on the device, the in-place inner product behind
+    fidelity / expectation_value with two DIFFERENT physical layouts, entangle(q, q), and the clone."""
+    rng = np.random.default_rng(77)
+    n = 18
+    # a sparse state: GHZ-like superposition of 5 basis states with random amplitudes, scrambled by relabels
+    idx = np.sort(rng.choice(1 << n, size=5, replace=False))
+    amps = rng.normal(size=5) + 1j * rng.normal(size=5)
+    amps /= np.linalg.norm(amps)
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[idx] = amps
+    sv, orc = _sv(psi), OracleStatevector(psi)
+    perm = [int(x) for x in rng.permutation(n)]
+    sv.permute(perm)
+    orc.permute(perm)
+    sv.swap((0, 5))
+    orc.swap((0, 5))
+    flat = orc.flatten()
+    keep = np.flatnonzero(np.abs(flat) > 1e-8)
+    d = sv.to_dict()
+    assert list(d) == [format(int(i), f"0{n}b") for i in keep]
+    np.testing.assert_allclose(np.array(list(d.values())), flat[keep], atol=1e-14)
+    np.testing.assert_allclose(np.array(list(sv.to_prob_dict(encoding="LSB").values())), np.abs(flat[keep]) ** 2, atol=1e-14)
+    assert list(sv.to_prob_dict(encoding="LSB")) == [format(int(i), f"0{n}b")[::-1] for i in keep]
+    # dense state: more entries than the sparse buffer holds -> falls back to the full read-out, same answer
+    dense = rand_state(rng, 12)
+    small = _sv(dense)
+    small.SPARSE_CAP = 64
+    assert len(small.to_dict(atol=0.0)) == 1 << 12
+    # inner product of two registers with different layouts (one went through projections / relabels)
+    a = rand_state(rng, 14)
+    sa, sb = _sv(a, 15), _sv(a, 15)
+    pm = outcome_to_operator_matrix((0.6, 0.0, 0.8), 0)
+    for s in (sa, sb):
+        s.add_nodes(1, mbqc.BasicStates.PLUS)
+        s.entangle((14, 2))
+    sa.project_qubit(pm, 2)                 # layouts now differ: sa has a hole / a moved qubit
+    sb.permute([0, 1, 14, *range(3, 14), 2])
+    sb.project_qubit(pm, 14)
+    sb.permute([0, 1, 13, *range(2, 13)])    # bring the new qubit of sb where sa has it? (only the state matters)
+    oa = OracleStatevector(a, max_qubits=15)
+    oa.add_nodes(1, mbqc.BasicStates.PLUS)
+    oa.entangle((14, 2))
+    oa.project_qubit(pm, 2)
+    np.testing.assert_allclose(sa.flatten(), oa.flatten(), atol=1e-12)
+    assert abs(sa.fidelity(sb) - abs(np.vdot(sa.flatten(), sb.flatten())) ** 2) < 1e-12
+    op = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    assert abs(sa.expectation_value(op, [3, 9]) - oa.expectation_value(op, [3, 9])) < 1e-11
+    np.testing.assert_allclose(sa.flatten(), oa.flatten(), atol=1e-12)       # expectation_value left the state alone
+    # entangle(q, q) is Z on q in the reference kernel (statevec.py:930-937)
+    sa.entangle((4, 4))
+    oa.evolve_single(mbqc.Ops.Z, 4)
+    np.testing.assert_allclose(sa.flatten(), oa.flatten(), atol=1e-12)
+
+
+def test_nonstrict_zero_norm_is_a_runtime_error_not_nan():
+    """An impossible branch in non-strict mode: the stored state stays finite and the FIRST error the caller sees is the
+    reference's RuntimeError (statevec.py:1192-1193), whatever is asked next."""
+    for batch in (0, 4):
+        sv = B200Statevector(nqubit=0, max_qubits=14, strict=False, batch=batch)
+        sv.add_nodes(12, mbqc.BasicStates.ZERO)
+        sv.add_nodes(1, mbqc.BasicStates.PLUS)
+        sv.entangle((0, 12))
+        sv.project_qubit(outcome_to_operator_matrix((0.0, 0.0, 1.0), 1), 0)      # |0> measured as 1: probability 0
+        sv.add_nodes(1, mbqc.BasicStates.PLUS)
+        sv.entangle((1, 12))
+        sv.project_qubit(outcome_to_operator_matrix((1.0, 0.0, 0.0), 0), 1)
+        p = sv.expectation_single(outcome_to_operator_matrix((1.0, 0.0, 0.0), 0), 3)
+        assert np.isfinite(p.real) and abs(p.imag) <= 1e-10          # no NaN reaches f_expectation0's assertion
+        with pytest.raises(RuntimeError):
+            sv.sync()
