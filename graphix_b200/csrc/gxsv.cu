@@ -29,9 +29,9 @@ namespace {
 constexpr int HOLE_MIN = 8;     // dead bits are only ever created at physical bit >= HOLE_MIN
 constexpr int TILE_BITS = 11;   // k_contract<4,true>: a CTA tile spans the lowest 11 live bits
 constexpr int U_DEF = 4;
-constexpr int RING = 4096;    // result slots (128 B each, pinned + mapped)
+constexpr int RING = 4096;    // result slots (256 B each, pinned + mapped)
 constexpr int GXSV_VERSION = 100;
-constexpr int MAX_BATCH_AXES = 6;  // distinct physical bits one batched pass may act on (GXSV_BATCH_AXES = 1..6).
+constexpr int MAX_BATCH_AXES = 6;  // distinct physical bits one batched pass may act on (GXSV_BATCH_AXES = 1..7).
 // Up to 3 axes run in k_fused_batch (2^3 amplitudes per thread in registers, 4 CTAs per SM); 4..6 axes run in
 // k_fused_tile, which keeps three axes at a time in registers and transposes the CTA tile through shared memory
 // between phases.  (Round 1 measured a 4-axis all-register pass: 128 registers, 2 CTAs per SM, 0.64 of the copy rate.)
@@ -62,7 +62,7 @@ struct StageNote {
 struct Deferred {
   unsigned long long first = 0;   // result slot
   int second = 0;                 // stages
-  StageNote note[8];
+  StageNote note[MAX_STAGES];
 };
 
 }  // namespace
@@ -95,13 +95,15 @@ struct gxsv {
   int profile = 0;
   int batch_axes = MAX_BATCH_AXES;   // distinct physical bits per batched pass (GXSV_BATCH_AXES)
   int chunk_log2 = DEFAULT_CHUNK_LOG2;
+  int tile_regs = 4;       // register axes per phase of k_fused_tile (GXSV_TILE_REGS = 3 | 4; measured on config 2: 4 ->
+                           // 0.378 ms per pass / 44.8 k commands/s, 3 -> 0.518 ms / 32.9 k)
   int analytic_norms = 1;  // skip the norm accumulation of stages whose outcome probability is known to be 1/2
   int use_tma = 0;         // 1: batched passes stage CTA tiles through shared memory with bulk copies (k_fused_tma; measured slower for many
                            // stages per pass, see kernels.cuh) when the layout allows
   int batch_max = 0;       // > 0: queue up to this many fused projections and run them in one pass (non-strict only)
   Batch batch;             // the open batch (nstages == 0: none)
   std::vector<Deferred> deferred;   // projections awaiting their norm check (non-strict mode)
-  StageNote open_notes[8];          // notes of the stages in the open batch
+  StageNote open_notes[MAX_STAGES]; // notes of the stages in the open batch
   int dist = 0;            // sharded: projections publish local norms, the host sets g after the all-reduce
   int sm_count = 148;
   gxsv_stats_t stats;
@@ -109,6 +111,11 @@ struct gxsv {
   std::vector<cudaEvent_t> ev_pool;
   std::string err;
   // peer registers of the ranks this shard exchanges with (CUDA IPC mappings, one slot per rank-index bit)
+  // Pauli frame of pending X / Z byproducts on materialised qubits (physical-bit masks, lazy mode only):
+  // true state = prod_q Z_q^{fz_q} X_q^{fx_q} applied to what the register (plus its queued work) holds.  X and Z at the
+  // end of a pattern then cost no pass: read-outs apply the frame on the fly, anything else makes it real first.
+  uint64_t fx = 0, fz = 0;
+  bool lazy_frame = true;
   double2* peer_psi[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double2* exported_psi = nullptr;
 };
@@ -186,6 +193,7 @@ cudaEvent_t get_event(gxsv_t* h) {
 }
 
 int flush_batch(gxsv_t* h);
+int settle_frame(gxsv_t* h);
 thread_local TmaBatch g_tma;        // scratch of flush_batch (kernel parameters are copied at launch)
 thread_local Holes g_tma_holes;
 
@@ -193,8 +201,9 @@ struct Launch {
   gxsv_t* h;
   int kind;
   cudaEvent_t e0 = nullptr;
-  Launch(gxsv_t* h_, int kind_, double bytes) : h(h_), kind(kind_) {
+  Launch(gxsv_t* h_, int kind_, double bytes, bool frame_aware = false) : h(h_), kind(kind_) {
     if (h->batch.nstages) flush_batch(h);   // queued projections go first: everything else sees their result
+    if (!frame_aware && (h->fx | h->fz)) settle_frame(h);   // then the pending X / Z byproducts, made real
     h->stats.launches[kind] += 1;
     h->stats.algo_bytes[kind] += bytes;
     if (h->profile) {
@@ -230,7 +239,7 @@ Res* next_slot(gxsv_t* h, unsigned long long* seq_out) {
   return h->ring_dev + (h->seq % RING);
 }
 
-int wait_slot(gxsv_t* h, unsigned long long seq, double out[8]) {
+int wait_slot(gxsv_t* h, unsigned long long seq, double out[RES_VALUES]) {
   volatile Res* r = h->ring_host + (seq % RING);
   unsigned long spins = 0;
   while (r->seq != seq) {
@@ -246,7 +255,7 @@ int wait_slot(gxsv_t* h, unsigned long long seq, double out[8]) {
     }
   }
   __sync_synchronize();
-  for (int i = 0; i < 8; ++i) out[i] = r->v[i];
+  for (int i = 0; i < RES_VALUES; ++i) out[i] = r->v[i];
   return GXSV_OK;
 }
 
@@ -259,14 +268,14 @@ int check_launch(gxsv_t* h, const char* what) {
 // Sign table of a stage acting on register axis `la` of `nb` register axes (physical bits regbit[]): byte k = 0x80 iff
 // the k-th amplitude pair (slot lo = k with a zero bit inserted at position la) has odd parity of
 // (physical bits of the register axes set in lo) & mask.
-unsigned int parity_table(uint64_t mask, const unsigned char* regbit, int nb, int la) {
-  unsigned int t = 0;
+unsigned long long parity_table(uint64_t mask, const unsigned char* regbit, int nb, int la) {
+  unsigned long long t = 0;
   for (int k = 0; k < (1 << (nb - 1)); ++k) {
     const int lo = ((k >> la) << (la + 1)) | (k & ((1 << la) - 1));
     int par = 0;
     for (int i = 0; i < nb; ++i)
       if (((lo >> i) & 1) && ((mask >> regbit[i]) & 1ull)) par ^= 1;
-    if (par) t |= 0x80u << (8 * k);
+    if (par) t |= 0x80ull << (8 * k);
   }
   return t;
 }
@@ -275,40 +284,40 @@ unsigned int parity_table(uint64_t mask, const unsigned char* regbit, int nb, in
 // acts on at most three distinct batch axes (those are held in registers, k_fused_tile).  Returns the number of
 // phases (out may be NULL: the queueing code only asks whether one more stage still fits MAX_PHASES).  With `out`,
 // also tabulates the offsets the kernel addresses with.
-int plan_phases(const Batch& bt, TileBatch* out) {
+int plan_phases(const Batch& bt, TileBatch* out, int R) {
   int nph = 0;
   int i = 0;
-  const int A = bt.naxes, F = WTILE_LOG2 - A;
+  const int A = bt.naxes, F = (5 + R) - A;
   while (i < bt.nstages) {
-    int T[3], nt = 0, j = i;
+    int T[4], nt = 0, j = i;
     for (; j < bt.nstages; ++j) {
       const int a = bt.st[j].axis;
       bool in = false;
       for (int k = 0; k < nt; ++k) in = in || (T[k] == a);
       if (in) continue;
-      if (nt == 3) break;
+      if (nt == R) break;
       T[nt++] = a;
     }
     if (out && nph < MAX_PHASES) {
-      // pad the register set to three axes with batch axes that the phase does not use
-      for (int a = 0; a < A && nt < 3; ++a) {
+      // pad the register set to R axes with batch axes that the phase does not use
+      for (int a = 0; a < A && nt < R; ++a) {
         bool in = false;
         for (int k = 0; k < nt; ++k) in = in || (T[k] == a);
         if (!in) T[nt++] = a;
       }
-      std::sort(T, T + 3);
-      int oth[3], no = 0;
+      std::sort(T, T + R);
+      int oth[4], no = 0;
       for (int a = 0; a < A; ++a) {
         bool in = false;
-        for (int k = 0; k < 3; ++k) in = in || (T[k] == a);
+        for (int k = 0; k < R; ++k) in = in || (T[k] == a);
         if (!in) oth[no++] = a;
       }
-      unsigned char regbit[3];
-      for (int k = 0; k < 3; ++k) regbit[k] = bt.axbit[T[k]];
-      for (int b = 0; b < 8; ++b) {
+      unsigned char regbit[4];
+      for (int k = 0; k < R; ++k) regbit[k] = bt.axbit[T[k]];
+      for (int b = 0; b < (1 << R); ++b) {
         uint64_t go = 0;
         unsigned int so = 0;
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < R; ++k)
           if ((b >> k) & 1) { go |= 1ull << regbit[k]; so |= 1u << T[k]; }
         out->gbits[nph][b] = go;
         out->sbits[nph][b] = (unsigned short)(so << F);
@@ -321,10 +330,10 @@ int plan_phases(const Batch& bt, TileBatch* out) {
       out->s_end[nph] = (unsigned char)j;
       for (int s = i; s < j; ++s) {
         int la = 0;
-        for (int k = 0; k < 3; ++k) if (T[k] == bt.st[s].axis) la = k;
+        for (int k = 0; k < R; ++k) if (T[k] == bt.st[s].axis) la = k;
         out->lax[s] = (unsigned char)la;
-        out->st[s].qtab = parity_table(bt.st[s].mq, regbit, 3, la);
-        out->st[s].vtab = parity_table(bt.st[s].mv, regbit, 3, la);
+        out->st[s].qtab = parity_table(bt.st[s].mq, regbit, R, la);
+        out->st[s].vtab = parity_table(bt.st[s].mv, regbit, R, la);
       }
     }
     nph += 1;
@@ -441,7 +450,7 @@ int flush_batch(gxsv_t* h) {
       if (st.kind == 0) { m00 = one; m01 = st.a; m10 = make_double2(rho, 0.0); m11 = make_double2(-ra.x, -ra.y); }
       else { m00 = st.a; m01 = one; m10 = ra; m11 = make_double2(-rho, 0.0); }
     }
-    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
+    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n), /*frame_aware=*/true);   // a pending frame was issued AFTER these stages
     k_fused<U_DEF><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, bt.axbit[0], m00, m01, m10, m11, st.mq,
                                                                     st.mv, npair, h->partials, h->ctrl, slot, seq,
                                                                     h->dist ? FIN_ONESHOT : FIN_CONTRACT, bt.nscale[0]);
@@ -454,14 +463,15 @@ int flush_batch(gxsv_t* h) {
       attr_set = true;
     }
     const uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * 2);   // persistent: 2 resident CTAs per SM
-    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
+    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n), /*frame_aware=*/true);   // a pending frame was issued AFTER these stages
     k_fused_tma<<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, g_tma_holes, g_tma, ntiles, h->partials, h->ctrl, slot, seq, fm);
-  } else if (bt.naxes <= 3) {
+  } else if (bt.naxes <= 3 || bt.naxes > h->tile_regs + 3 || n < 8 + h->tile_regs + 1) {
+    if (bt.naxes > 3) return fail(h, GXSV_EVALUE, "internal: batch on %d axes cannot run", bt.naxes);
     for (int k = 0; k < bt.nstages; ++k) {
       bt.st[k].qtab = parity_table(bt.st[k].mq, bt.axbit, bt.naxes, bt.st[k].axis);
       bt.st[k].vtab = parity_table(bt.st[k].mv, bt.axbit, bt.naxes, bt.st[k].axis);
     }
-    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
+    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n), /*frame_aware=*/true);   // a pending frame was issued AFTER these stages
     // chunked CTA -> index mapping only when every CTA still gets >= 8 chunks (else plain grid stride)
     int gl = h->chunk_log2;
     while (gl > 0 && (ngroups >> (8 + gl)) < (uint64_t)grid * 8) --gl;
@@ -474,20 +484,23 @@ int flush_batch(gxsv_t* h) {
     tb.nstages = bt.nstages;
     tb.naxes = bt.naxes;
     for (int k = 0; k < bt.nstages; ++k) { tb.st[k] = bt.st[k]; tb.nscale[k] = bt.nscale[k]; }
-    tb.nphases = plan_phases(bt, &tb);
+    const int R = h->tile_regs;
+    tb.nphases = plan_phases(bt, &tb, R);
     if (tb.nphases > MAX_PHASES) return fail(h, GXSV_EVALUE, "internal: batch needs %d phases", tb.nphases);
-    const uint64_t ntiles = 1ull << (n - TILE_LOG2);
-    const size_t dyn = sizeof(double2) << TILE_LOG2;
+    const uint64_t ntiles = 1ull << (n - (8 + R));            // CTA iterations: 8 warp tiles of 2^(5+R) amplitudes
+    const size_t dyn = sizeof(double2) << (8 + R);
     static bool attr_set = false;
     if (!attr_set) {
-      CU(cudaFuncSetAttribute(k_fused_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      CU(cudaFuncSetAttribute(k_fused_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 11)));
+      CU(cudaFuncSetAttribute(k_fused_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 12)));
       attr_set = true;
     }
-    uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * 4);   // persistent: 4 resident CTAs per SM
+    uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * (R == 3 ? 4 : 2));   // persistent: resident CTAs only
     int gl = h->chunk_log2;
     while (gl > 0 && (ntiles >> gl) < tgrid * 8) --gl;
-    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n));
-    k_fused_tile<<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm);
+    Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n), /*frame_aware=*/true);   // a pending frame was issued AFTER these stages
+    if (R == 3) k_fused_tile<3><<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm);
+    else k_fused_tile<4><<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm);
   }
   Deferred d;
   d.first = seq;
@@ -505,7 +518,7 @@ int check_deferred(gxsv_t* h) {
   std::vector<Deferred> todo;
   todo.swap(h->deferred);
   for (auto& d : todo) {
-    double v[8];
+    double v[RES_VALUES];
     rc = wait_slot(h, d.first, v);
     if (rc) return rc;
     double prev = 1.0;
@@ -524,6 +537,32 @@ int check_deferred(gxsv_t* h) {
     }
   }
   return GXSV_OK;
+}
+
+// Make the pending Pauli frame real: one swap pass for all X flips, one sign pass for all Z's (X first: the frame is
+// kept in the order Z^z X^x per qubit).
+int settle_frame(gxsv_t* h) {
+  if (!(h->fx | h->fz)) return GXSV_OK;
+  const uint64_t fx = h->fx, fz = h->fz;
+  h->fx = h->fz = 0;                         // cleared first: the launches below go through Launch
+  const int n = nlive_bits(h);
+  const double S = 16.0 * std::ldexp(1.0, n);
+  if (fx && n >= 1) {
+    const int b0 = __builtin_ctzll(fx);
+    Holes hs = make_holes(h, b0);
+    const uint64_t npair = 1ull << (n - 1);
+    Launch L(h, GXSV_K_APPLY1Q, 2.0 * S);
+    k_xflip<U_DEF><<<grid_for(h, npair, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, fx, npair);
+  }
+  if (fz) {
+    Holes hs = make_holes(h);
+    static thread_local EdgeList el;
+    el.n = 0;
+    const uint64_t nlive = 1ull << n;
+    Launch L(h, GXSV_K_APPLY1Q, S);
+    k_diag_edges<U_DEF><<<grid_for(h, nlive, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, el, fz, nlive);
+  }
+  return check_launch(h, "settle_frame");
 }
 
 void trim_extent(gxsv_t* h) {
@@ -808,7 +847,7 @@ int init_common(gxsv_t* h) {
   CU(cudaGetDeviceProperties(&prop, h->device));
   h->sm_count = prop.multiProcessorCount;
   CU(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
-  CU(cudaMalloc(&h->partials, sizeof(double) * 8 * (size_t)(h->sm_count * 8 + 8)));
+  CU(cudaMalloc(&h->partials, sizeof(double) * RES_VALUES * (size_t)(h->sm_count * 8 + 8)));
   CU(cudaMalloc(&h->tabs_dev, sizeof(GatherTables)));
   CU(cudaMalloc(&h->op_dev, sizeof(double2) * 256));
   CU(cudaHostAlloc(&h->ring_host, sizeof(Res) * RING, cudaHostAllocMapped));
@@ -863,6 +902,8 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
     if (v >= 1 && v <= MAX_TILE_AXES) h->batch_axes = v;
   }
   if (const char* tm = std::getenv("GXSV_TMA")) h->use_tma = std::atoi(tm) ? 1 : 0;
+  if (const char* lf = std::getenv("GXSV_LAZY_FRAME")) h->lazy_frame = std::atoi(lf) != 0;
+  if (const char* tr = std::getenv("GXSV_TILE_REGS")) h->tile_regs = (std::atoi(tr) == 3) ? 3 : 4;
   if (const char* an = std::getenv("GXSV_ANALYTIC_NORMS")) h->analytic_norms = std::atoi(an) ? 1 : 0;
   if (const char* cl = std::getenv("GXSV_CHUNK_LOG2")) {
     const int v = std::atoi(cl);
@@ -943,6 +984,7 @@ int gxsv_reset(gxsv_t* h) {
   h->phys_bits = 0;
   h->live_mask = 0;
   h->hscale = 1.0;
+  h->fx = h->fz = 0;
   const double2 one = make_double2(1.0, 0.0);
   const Ctrl c0 = {1.0, 0u, 0u};
   CU(cudaMemcpyAsync(h->psi, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
@@ -984,6 +1026,11 @@ int gxsv_set_option(gxsv_t* h, int key, int value) {
     case GXSV_OPT_TMA:
       h->use_tma = value ? 1 : 0;
       return GXSV_OK;
+    case GXSV_OPT_TILE_REGS:
+      if (value != 3 && value != 4) return fail(h, GXSV_EVALUE, "tile register axes must be 3 or 4");
+      { int rc = flush_batch(h); if (rc) return rc; }
+      h->tile_regs = value;
+      return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -998,6 +1045,7 @@ int gxsv_get_option(gxsv_t* h, int key, int* value) {
     case GXSV_OPT_BATCH_AXES: *value = h->batch_axes; return GXSV_OK;
     case GXSV_OPT_CHUNK_LOG2: *value = h->chunk_log2; return GXSV_OK;
     case GXSV_OPT_TMA: *value = h->use_tma; return GXSV_OK;
+    case GXSV_OPT_TILE_REGS: *value = h->tile_regs; return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -1143,6 +1191,23 @@ int gxsv_evolve_single(gxsv_t* h, int q, const double m[8]) {
       qb.s1 = m10 * a + m11 * b;
       return GXSV_OK;
     }
+    const bool is_x = (m00 == cplx(0.0) && m11 == cplx(0.0) && m01 == m10 && std::abs(m01) > 0.0);
+    const bool is_z = diagonal && m11 == -m00 && std::abs(m00) > 0.0;
+    if (qb.phys >= 0 && h->lazy_frame && (is_x || is_z)) {
+      // byproduct on a materialised qubit: goes to the Pauli frame, no pass (c * X after Z^z X^x = (-1)^z c Z^z X^(x+1))
+      if (is_x) {
+        rc = settle(h, q);                   // CZs queued on q do not commute with X: they go first
+        if (rc) return rc;
+        const uint64_t bit = 1ull << h->q[q].phys;
+        if (h->fz & bit) h->hscale = -h->hscale;
+        h->fx ^= bit;
+        h->hscale *= m01;
+      } else {
+        h->fz ^= 1ull << qb.phys;
+        h->hscale *= m00;
+      }
+      return GXSV_OK;
+    }
     if (qb.phys < 0 || !diagonal) rc = settle(h, q);
   } else {
     rc = flush_pending(h);
@@ -1229,6 +1294,11 @@ int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) 
   CU(cudaSetDevice(h->device));
   int rc = check_q(h, q);
   if (rc) return rc;
+  if (h->fx | h->fz) {
+    rc = flush_batch(h);
+    if (!rc) rc = settle_frame(h);
+    if (rc) return rc;
+  }
   if (h->fusion >= 2 && h->q[q].phys < 0) {
     rc = materialize(h, q);   // the measured qubit itself must exist; its CZ partners need not
     if (rc) return rc;
@@ -1286,7 +1356,7 @@ int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) 
         }
         rc = check_launch(h, "k_pair_reduce");
         if (rc) return rc;
-        double v[8];
+        double v[RES_VALUES];
         rc = wait_slot(h, seq, v);
         if (rc) return rc;
         out[0] = w_even * v[0] + w_odd * v[1];
@@ -1311,7 +1381,7 @@ int gxsv_expectation_single(gxsv_t* h, int q, const double m[8], double out[2]) 
   }
   rc = check_launch(h, "k_pair_reduce");
   if (rc) return rc;
-  double v[8];
+  double v[RES_VALUES];
   rc = wait_slot(h, seq, v);
   if (rc) return rc;
   out[0] = v[0];
@@ -1323,12 +1393,18 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
   CU(cudaSetDevice(h->device));
   int rc = check_q(h, q);
   if (rc) return rc;
+  if (h->fx | h->fz) {
+    // a projection may be queued without any launch: pending byproducts were issued earlier and must act first
+    rc = flush_batch(h);
+    if (!rc) rc = settle_frame(h);
+    if (rc) return rc;
+  }
   const cplx m00(m[0], m[1]), m01(m[2], m[3]), m10(m[4], m[5]), m11(m[6], m[7]);
   const double r0 = std::norm(m00) + std::norm(m01), r1 = std::norm(m10) + std::norm(m11);
   if (r0 + r1 == 0.0) return fail(h, GXSV_EZERONORM, "Attempted to remove qubit %d from 0-norm statevector.", q);
   const double det = std::abs(m00 * m11 - m01 * m10);
   const bool rank1 = det <= 1e-13 * (r0 + r1);
-  double v[8];
+  double v[RES_VALUES];
   unsigned long long seq;
   if (rank1) {
     // op = u w^T: row r = u_r * w.  Contract with the larger row (best conditioned); the two half-norms the
@@ -1391,14 +1467,14 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           int ax = -1;
           for (int a = 0; a < h->batch.naxes; ++a) if (h->batch.axbit[a] == p) ax = a;
           // more than three axes need a CTA tile of 2^11 amplitudes (k_fused_tile)
-          const int max_axes = (nlive_bits(h) >= TILE_LOG2 + 1) ? h->batch_axes : std::min(h->batch_axes, 3);
+          const int max_axes = (nlive_bits(h) >= 8 + h->tile_regs + 1) ? h->batch_axes : std::min(h->batch_axes, 3);
           bool full = h->batch.nstages >= std::min(h->batch_max, (int)MAX_STAGES) || (ax < 0 && h->batch.naxes >= max_axes);
           if (!full && h->batch.naxes + (ax < 0 ? 1 : 0) > 3) {
             // would the batch with this stage still fit MAX_PHASES register phases?
             Batch& b = h->batch;
             b.st[b.nstages].axis = (ax < 0) ? b.naxes : ax;
             b.nstages += 1;
-            full = plan_phases(b, nullptr) > MAX_PHASES;
+            full = plan_phases(b, nullptr, h->tile_regs) > MAX_PHASES;
             b.nstages -= 1;
           }
           if (full) {
@@ -1561,8 +1637,9 @@ int gxsv_permute(gxsv_t* h, const int* perm, int n) {
 }
 
 static int gather_chunk(gxsv_t* h, double2* out, uint64_t first, uint64_t count) {
-  Launch L(h, GXSV_K_GATHER, 32.0 * (double)count);
-  k_gather<<<grid_for(h, count, 4), TPB, 0, h->stream>>>(h->psi, out, h->tabs_dev, first, count, d2(h->hscale), h->ctrl);
+  Launch L(h, GXSV_K_GATHER, 32.0 * (double)count, /*frame_aware=*/true);
+  k_gather<<<grid_for(h, count, 4), TPB, 0, h->stream>>>(h->psi, out, h->tabs_dev, first, count, d2(h->hscale), h->ctrl,
+                                                          h->fx, h->fz);
   return GXSV_OK;
 }
 
@@ -1612,13 +1689,13 @@ int gxsv_norm2(gxsv_t* h, double* out) {
   unsigned long long seq;
   Res* slot = next_slot(h, &seq);
   {
-    Launch L(h, GXSV_K_EXPECT, state_bytes(h));
+    Launch L(h, GXSV_K_EXPECT, state_bytes(h), /*frame_aware=*/true);   // |amplitudes| do not see X / Z
     k_norm2<U_DEF><<<grid_for(h, nlive, U_DEF), TPB, 0, h->stream>>>(h->psi, hs, nlive, h->partials, h->ctrl, slot, seq,
                                                                     std::norm(h->hscale));
   }
   rc = check_launch(h, "k_norm2");
   if (rc) return rc;
-  double v[8];
+  double v[RES_VALUES];
   rc = wait_slot(h, seq, v);
   if (rc) return rc;
   *out = v[0];
@@ -1647,13 +1724,13 @@ static int inner_in_place(gxsv_t* a, gxsv_t* b, double out[2]) {
   unsigned long long seq;
   Res* slot = next_slot(a, &seq);
   {
-    Launch L(a, GXSV_K_EXPECT, 32.0 * (double)total);
+    Launch L(a, GXSV_K_EXPECT, 32.0 * (double)total, /*frame_aware=*/true);
     k_inner_gather<<<grid_for(a, total, 4), TPB, 0, a->stream>>>(a->psi, a->tabs_dev, b->psi, b->tabs_dev, total,
-                                                                   a->partials, a->ctrl, slot, seq);
+                                                                   a->partials, a->ctrl, slot, seq, a->fx, a->fz, b->fx, b->fz);
   }
   int rc = check_launch(a, "k_inner_gather");
   if (rc) return rc;
-  double v[8];
+  double v[RES_VALUES];
   rc = wait_slot(a, seq, v);
   if (rc) return rc;
   const cplx z = cplx(v[0], v[1]) * std::conj(a->hscale * ca.g) * (b->hscale * cb.g);
@@ -1687,6 +1764,8 @@ int gxsv_clone(gxsv_t* h, gxsv_t** out) {
   c->phys_bits = h->phys_bits;
   c->live_mask = h->live_mask;
   c->hscale = h->hscale;
+  c->fx = h->fx;
+  c->fz = h->fz;
   cudaError_t e = cudaMemcpyAsync(c->psi, h->psi, sizeof(double2) << h->phys_bits, cudaMemcpyDeviceToDevice, h->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(c->ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToDevice, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -1712,9 +1791,9 @@ int gxsv_nonzero(gxsv_t* h, double atol, unsigned long long cap, unsigned long l
   cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), h->stream);
   const uint64_t total = 1ull << h->q.size();
   {
-    Launch L(h, GXSV_K_GATHER, 16.0 * (double)total);
+    Launch L(h, GXSV_K_GATHER, 16.0 * (double)total, /*frame_aware=*/true);
     k_nonzero<<<grid_for(h, total, 4), TPB, 0, h->stream>>>(h->psi, h->tabs_dev, total, d2(h->hscale), h->ctrl, atol, dcount,
-                                                             didx, damp, cap);
+                                                             didx, damp, cap, h->fx, h->fz);
   }
   rc = check_launch(h, "k_nonzero");
   unsigned long long n = 0;
@@ -1785,7 +1864,7 @@ int gxsv_dm_trace_expect(gxsv_t* h, int npairs, const int* rows, const int* cols
   }
   rc = check_launch(h, "k_dm_diag");
   if (rc) return rc;
-  double v[8];
+  double v[RES_VALUES];
   rc = wait_slot(h, seq, v);
   if (rc) return rc;
   for (int i = 0; i < 4; ++i) out[i] = v[i];
@@ -1831,7 +1910,7 @@ int gxsv_take_norms(gxsv_t* h, double* out, int cap, int* count) {
   if (rc) return rc;
   int n = 0;
   for (auto& d : h->deferred) {
-    double v[8];
+    double v[RES_VALUES];
     rc = wait_slot(h, d.first, v);
     if (rc) return rc;
     for (int k = 0; k < d.second; ++k) {
@@ -1931,14 +2010,16 @@ int gxsv_ipc_close(gxsv_t* h) {
 
 int gxsv_flush_batch(gxsv_t* h) {
   CU(cudaSetDevice(h->device));
-  return flush_batch(h);
+  int rc = flush_batch(h);
+  if (!rc) rc = settle_frame(h);     // pending byproducts too: the partner is about to read this register
+  return rc;
 }
 
 int gxsv_swap_peer(gxsv_t* h, int q, int slot, int my_bit, double fre, double fim) {
   CU(cudaSetDevice(h->device));
   int rc = check_q(h, q);
   if (rc) return rc;
-  if (h->batch.nstages)
+  if (h->batch.nstages || (h->fx | h->fz))
     return fail(h, GXSV_EVALUE, "swap_peer: queued projections must be launched (gxsv_flush_batch) before the barrier that precedes the swap");
   if (slot < 0 || slot >= 8 || !h->peer_psi[slot]) return fail(h, GXSV_EVALUE, "swap_peer: no peer register in slot %d", slot);
   if (h->exported_psi != h->psi) return fail(h, GXSV_EVALUE, "swap_peer: the register moved since it was exported");

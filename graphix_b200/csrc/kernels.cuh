@@ -35,10 +35,11 @@ struct Ctrl {            // device-resident control block
   unsigned int pad;
 };
 
-struct Res {             // one slot of the host-mapped result ring
-  double v[8];
+constexpr int RES_VALUES = 16;
+struct Res {             // one slot of the host-mapped result ring (256 B)
+  double v[RES_VALUES];
   unsigned long long seq;
-  unsigned long long pad[7];
+  unsigned long long pad[15];
 };
 
 __device__ __forceinline__ uint64_t expand(uint64_t x, const Holes& h) {
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(TPB) k_fused(double2* __restrict__ psi, const 
 // 0.540 ms per pass);
 // with 3 stages the pass runs at ~0.84 of the copy rate with the FP64 pipe ~45 % busy under the 1 kW power cap.
 // ---------------------------------------------------------------------------
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 // One fused (N, E.., M) stage on one axis.  With <c| the measurement bra (host scalar folded in), (s0, s1) the state of
 // the partner v and sq / sv the CZ signs of the measured qubit / of v (k_fused above):
 //   r0 = s0 (c0 t0 + c1 t1),   r1 = sv s1 (c0 t0 - c1 t1),      t0 = psi[.., 0], t1 = sq psi[.., 1].
@@ -407,7 +408,7 @@ struct Stage {
   unsigned char neg;             // kinds 0/1: s1 = -s0
   unsigned char acc;             // 1 = accumulate the norm^2 after this stage (0: the host knows it analytically)
   unsigned char pad;
-  unsigned int qtab, vtab;       // set when the pass is launched (depend on the register assignment of the axes):
+  unsigned long long qtab, vtab; // set when the pass is launched (depend on the register assignment of the axes):
                                  // byte k = 0x80 iff the k-th amplitude pair of the stage's axis takes the sign
 };
 struct Batch {
@@ -427,15 +428,17 @@ __device__ __forceinline__ double flip_sign(const double x, const unsigned int s
 // prepared in |+> — the norm after the stage is exactly 2 |in|^2 whatever the data (the outcome probability of such a
 // measurement is 1/2), so the host asks for the accumulation only where it cannot know the answer (Stage::acc).
 template <int NB, int AX, int KIND, bool ACC>
-__device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& st, const unsigned int tq,
-                                            const unsigned int tv, double& nrm0, double& nrm1) {
+__device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& st, const unsigned long long tq64,
+                                            const unsigned long long tv64, double& nrm0, double& nrm1) {
   const double2 a = st.a;
 #pragma unroll
   for (int lo = 0; lo < (1 << NB); ++lo) {
     if ((lo >> AX) & 1) continue;
     const int hi = lo | (1 << AX);
     const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded at compile time)
-    const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | (k << 12)), sv = __byte_perm(tv, 0u, 0x0444 | (k << 12));
+    const unsigned int tq = (k < 4) ? (unsigned int)tq64 : (unsigned int)(tq64 >> 32);
+    const unsigned int tv = (k < 4) ? (unsigned int)tv64 : (unsigned int)(tv64 >> 32);
+    const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | ((k & 3) << 12)), sv = __byte_perm(tv, 0u, 0x0444 | ((k & 3) << 12));
     double2 r0, r1;
     if (KIND == 0) {
       double2 w = cmul(a, v[hi]);
@@ -470,8 +473,8 @@ template <int NB, int AX>
 __device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage& st, const unsigned int gpar_q,
                                               const unsigned int gpar_v, double& nrm0, double& nrm1) {
   // byte k of tq / tv = 0x80 iff the k-th amplitude pair takes the sign
-  const unsigned int tq = st.qtab ^ ((gpar_q & 1u) ? 0x80808080u : 0u);
-  const unsigned int tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x80808080u : 0u);
+  const unsigned long long tq = st.qtab ^ ((gpar_q & 1u) ? 0x8080808080808080ull : 0ull);
+  const unsigned long long tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x8080808080808080ull : 0ull);
   if (st.kind == 0) {
     if (st.acc) stage_pairs<NB, AX, 0, true>(v, st, tq, tv, nrm0, nrm1);
     else stage_pairs<NB, AX, 0, false>(v, st, tq, tv, nrm0, nrm1);
@@ -556,29 +559,34 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_batch(double2* __restrict__ ps
 // ---------------------------------------------------------------------------
 constexpr int TILE_LOG2 = 11;      // amplitudes per CTA iteration
 constexpr int WTILE_LOG2 = 8;      // amplitudes per warp tile
-constexpr int MAX_TILE_AXES = 6;
+constexpr int MAX_TILE_AXES = 7;
 constexpr int MAX_PHASES = 4;
 struct TileBatch {
   int nstages, naxes, nphases, pad;
-  unsigned char lax[MAX_STAGES];              // register slot (0..2) of the axis of every stage inside its phase
+  unsigned char lax[MAX_STAGES];              // register slot (0..R-1) of the axis of every stage inside its phase
   unsigned char s_begin[MAX_PHASES], s_end[MAX_PHASES];
-  // everything a thread needs to address its 2^3 amplitudes is tabulated by the host (no per-tile index arithmetic):
-  unsigned long long gbits[MAX_PHASES][8];    // physical offset of register slot b in phase p
+  // everything a thread needs to address its 2^R amplitudes is tabulated by the host (no per-tile index arithmetic):
+  unsigned long long gbits[MAX_PHASES][16];   // physical offset of register slot b in phase p
   unsigned long long goth[MAX_PHASES][4];     // physical offset of the i-th axis fixed per lane (taken iff bit i of r = lane >> F)
-  unsigned short sbits[MAX_PHASES][8];        // the same two as offsets inside the warp's shared-memory tile (<< F applied)
+  unsigned short sbits[MAX_PHASES][16];       // the same two as offsets inside the warp's shared-memory tile (<< F applied)
   unsigned short soth[MAX_PHASES][4];
   double nscale[MAX_STAGES];
   Stage st[MAX_STAGES];
 };
-__global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+// R = register axes per phase: 3 (2^3 amplitudes per thread, 64 registers, 4 CTAs per SM, warp tile 2^8) or 4 (2^4
+// amplitudes per thread, 128 registers, 2 CTAs per SM, warp tile 2^9: fewer phases, runs twice as long).
+template <int R>
+__global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* __restrict__ psi, const __grid_constant__ Holes hs,
                                                       const __grid_constant__ TileBatch bt, const uint64_t ntiles,
                                                       const int glog, double* __restrict__ partials, Ctrl* ctrl,
                                                       Res* res, const unsigned long long seq, const int fin_mode) {
-  extern __shared__ double2 tile_all[];             // 8 warps x 2^WTILE_LOG2 amplitudes (dynamic: 32 KB)
+  constexpr int WT = 5 + R;                         // log2 amplitudes per warp tile
+  constexpr int D = 1 << R;
+  extern __shared__ double2 tile_all[];             // 8 warps x 2^WT amplitudes (dynamic)
   __shared__ double sacc[MAX_STAGES][TPB];
-  const int F = WTILE_LOG2 - bt.naxes;
+  const int F = WT - bt.naxes;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double2* tile = tile_all + ((size_t)warp << WTILE_LOG2);
+  double2* tile = tile_all + ((size_t)warp << WT);
   const unsigned int f = lane & ((1u << F) - 1u);
   const int r = lane >> F;
   const double g = ctrl->g;
@@ -592,7 +600,7 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi
       if (t >= ntiles) break;
       const uint64_t wt = t * (TPB / 32) + warp;    // this warp's tile
       const uint64_t base = expand((wt << F) | f, hs);
-      double2 v[8];
+      double2 v[D];
       // offsets of the axis values fixed per lane: uniform table entries selected by the bits of r (a table indexed by
       // r itself — a per-thread index into the kernel parameters — faulted on sm_100a with CUDA 12.9 although the
       // emulated addresses were all in range; the uniform form costs three predicated ORs)
@@ -609,7 +617,7 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi
       {
         double2* src = psi + gthread;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
+        for (int b = 0; b < D; ++b) {
           const double2 a = ld_amp(src + bt.gbits[0][b]);
           v[b] = make_double2(g * a.x, g * a.y);    // the pending normalisation, once per pass
         }
@@ -621,9 +629,10 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi
           const unsigned int pq = __popcll(gthread & st.mq), pv = __popcll(gthread & st.mv);
           double n0 = 0.0, n1 = 0.0;
           const int la = bt.lax[s];
-          if (la == 0) stage_on_axis<3, 0>(v, st, pq, pv, n0, n1);
-          else if (la == 1) stage_on_axis<3, 1>(v, st, pq, pv, n0, n1);
-          else stage_on_axis<3, 2>(v, st, pq, pv, n0, n1);
+          if (la == 0) stage_on_axis<R, 0>(v, st, pq, pv, n0, n1);
+          else if (la == 1) stage_on_axis<R, 1>(v, st, pq, pv, n0, n1);
+          else if (R == 3 || la == 2) stage_on_axis<R, 2>(v, st, pq, pv, n0, n1);
+          else stage_on_axis<R, R - 1>(v, st, pq, pv, n0, n1);
           if (st.acc) sacc[s][tid] += n0 + n1;
         }
         if (p + 1 < nphases) {
@@ -633,14 +642,14 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_tile(double2* __restrict__ psi
           const unsigned int s_new = sthread;
           __syncwarp();                             // every lane has read its slots of the previous transpose
 #pragma unroll
-          for (int b = 0; b < 8; ++b) tile[s_old | bt.sbits[p][b]] = v[b];
+          for (int b = 0; b < D; ++b) tile[s_old | bt.sbits[p][b]] = v[b];
           __syncwarp();
 #pragma unroll
-          for (int b = 0; b < 8; ++b) v[b] = tile[s_new | bt.sbits[p + 1][b]];
+          for (int b = 0; b < D; ++b) v[b] = tile[s_new | bt.sbits[p + 1][b]];
         } else {
           double2* dst = psi + gthread;
 #pragma unroll
-          for (int b = 0; b < 8; ++b) st_amp(dst + bt.gbits[p][b], v[b]);
+          for (int b = 0; b < D; ++b) st_amp(dst + bt.gbits[p][b], v[b]);
         }
       }
     }
@@ -837,6 +846,35 @@ __global__ void __launch_bounds__(TPB) k_apply1q(double2* __restrict__ psi, cons
   }
 }
 
+// Pending X byproducts made real: psi[i] <-> psi[i ^ fx] for every i whose bit b0 (the lowest bit of fx) is 0.
+// One pass (reads S, writes S) for any number of flipped qubits.  `hs` = holes + {b0}.
+template <int U>
+__global__ void __launch_bounds__(TPB) k_xflip(double2* __restrict__ psi, const __grid_constant__ Holes hs,
+                                               const uint64_t fx, const uint64_t npair) {
+  const uint64_t chunk = (uint64_t)TPB * U;
+  for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < npair; base += (uint64_t)gridDim.x * chunk) {
+    double2 a[U], b[U];
+    uint64_t s[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t j = base + (uint64_t)u * TPB + threadIdx.x;
+      s[u] = expand(j, hs);
+      if (j < npair) {
+        a[u] = ld_amp(psi + s[u]);
+        b[u] = ld_amp(psi + (s[u] ^ fx));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t j = base + (uint64_t)u * TPB + threadIdx.x;
+      if (j < npair) {
+        st_amp(psi + s[u], b[u]);
+        st_amp(psi + (s[u] ^ fx), a[u]);
+      }
+    }
+  }
+}
+
 // diagonal 2x2 with m00 folded into the host scalar: psi[i|p] *= f.  Reads S/2, writes S/2.
 template <int U>
 __global__ void __launch_bounds__(TPB) k_scale_half(double2* __restrict__ psi, const __grid_constant__ Holes hs,
@@ -987,7 +1025,9 @@ struct GatherTables {
 };
 __global__ void __launch_bounds__(TPB) k_gather(const double2* __restrict__ psi, double2* __restrict__ out,
                                                 const GatherTables* __restrict__ tabs, const uint64_t first,
-                                                const uint64_t count, const double2 h, const Ctrl* ctrl) {
+                                                const uint64_t count, const double2 h, const Ctrl* ctrl,
+                                                const uint64_t fx, const uint64_t fz) {
+  // fx / fz: pending Pauli frame (physical-bit masks): true[i] = (-1)^{parity(p(i) & fz)} stored[p(i) ^ fx]
   __shared__ uint64_t st[5][256];
   for (int i = threadIdx.x; i < 5 * 256; i += TPB) st[i >> 8][i & 255] = tabs->t[i >> 8][i & 255];
   __syncthreads();
@@ -997,7 +1037,9 @@ __global__ void __launch_bounds__(TPB) k_gather(const double2* __restrict__ psi,
     const uint64_t i = first + k;
     const uint64_t p = st[0][i & 255] | st[1][(i >> 8) & 255] | st[2][(i >> 16) & 255] | st[3][(i >> 24) & 255] |
                        st[4][(i >> 32) & 255];
-    out[k] = cmul(f, __ldg(psi + p));
+    double2 a = cmul(f, __ldg(psi + (p ^ fx)));
+    if (__popcll(p & fz) & 1) { a.x = -a.x; a.y = -a.y; }
+    out[k] = a;
   }
 }
 
@@ -1006,7 +1048,8 @@ __global__ void __launch_bounds__(TPB) k_gather(const double2* __restrict__ psi,
 __global__ void __launch_bounds__(TPB) k_inner_gather(const double2* __restrict__ xa, const GatherTables* __restrict__ ta,
                                                       const double2* __restrict__ xb, const GatherTables* __restrict__ tb,
                                                       const uint64_t n, double* __restrict__ partials, Ctrl* ctrl,
-                                                      Res* res, const unsigned long long seq) {
+                                                      Res* res, const unsigned long long seq, const uint64_t fxa,
+                                                      const uint64_t fza, const uint64_t fxb, const uint64_t fzb) {
   __shared__ uint64_t sa[5][256];
   __shared__ uint64_t sb[5][256];
   for (int i = threadIdx.x; i < 5 * 256; i += TPB) {
@@ -1020,7 +1063,9 @@ __global__ void __launch_bounds__(TPB) k_inner_gather(const double2* __restrict_
                         sa[4][(i >> 32) & 255];
     const uint64_t pb = sb[0][i & 255] | sb[1][(i >> 8) & 255] | sb[2][(i >> 16) & 255] | sb[3][(i >> 24) & 255] |
                         sb[4][(i >> 32) & 255];
-    const double2 a = __ldg(xa + pa), b = __ldg(xb + pb);
+    const double2 a = __ldg(xa + (pa ^ fxa));
+    double2 b = __ldg(xb + (pb ^ fxb));
+    if ((__popcll(pa & fza) ^ __popcll(pb & fzb)) & 1) { b.x = -b.x; b.y = -b.y; }   // pending Pauli frames of both sides
     acc[0] += a.x * b.x + a.y * b.y;
     acc[1] += a.x * b.y - a.y * b.x;
   }
@@ -1034,7 +1079,7 @@ __global__ void __launch_bounds__(TPB) k_nonzero(const double2* __restrict__ psi
                                                  const uint64_t count, const double2 h, const Ctrl* ctrl,
                                                  const double atol, unsigned long long* __restrict__ counter,
                                                  unsigned long long* __restrict__ idx_out, double2* __restrict__ amp_out,
-                                                 const unsigned long long cap) {
+                                                 const unsigned long long cap, const uint64_t fx, const uint64_t fz) {
   __shared__ uint64_t st[5][256];
   for (int i = threadIdx.x; i < 5 * 256; i += TPB) st[i >> 8][i & 255] = tabs->t[i >> 8][i & 255];
   __syncthreads();
@@ -1043,7 +1088,8 @@ __global__ void __launch_bounds__(TPB) k_nonzero(const double2* __restrict__ psi
   for (uint64_t i = (uint64_t)blockIdx.x * TPB + threadIdx.x; i < count; i += (uint64_t)gridDim.x * TPB) {
     const uint64_t p = st[0][i & 255] | st[1][(i >> 8) & 255] | st[2][(i >> 16) & 255] | st[3][(i >> 24) & 255] |
                        st[4][(i >> 32) & 255];
-    const double2 a = cmul(f, __ldg(psi + p));
+    double2 a = cmul(f, __ldg(psi + (p ^ fx)));
+    if (__popcll(p & fz) & 1) { a.x = -a.x; a.y = -a.y; }
     if (sqrt(cnorm2(a)) > atol) {
       const unsigned long long slot = atomicAdd(counter, 1ull);
       if (slot < cap) {

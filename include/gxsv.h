@@ -58,8 +58,10 @@ enum {
                          * ONE pass over the register; zero-norm errors surface at gxsv_sync / gxsv_flatten */
   GXSV_OPT_BATCH_AXES = 6, /* tuning: distinct physical bits one batched pass may act on (1..6, default 6) */
   GXSV_OPT_CHUNK_LOG2 = 7, /* tuning: log2 of the consecutive blocks / tiles a CTA of a batched pass takes at a time */
-  GXSV_OPT_TMA = 8         /* 1 = batched passes stage CTA tiles through shared memory with bulk copies (cp.async.bulk +
+  GXSV_OPT_TMA = 8,        /* 1 = batched passes stage CTA tiles through shared memory with bulk copies (cp.async.bulk +
                             * mbarrier) whenever the layout allows; 0 (default) = register-staged kernels */
+  GXSV_OPT_TILE_REGS = 9   /* tuning: register axes per phase of the multi-axis batched pass: 3 (2^3 amplitudes per thread,
+                            * 4 CTAs per SM) or 4 (default: 2^4 per thread, 2 CTAs per SM, fewer phases) */
 };
 
 /* kernel kinds reported by gxsv_profile_read / gxsv_stats */

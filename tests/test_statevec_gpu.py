@@ -429,7 +429,7 @@ def test_large_state_roundtrip_properties():
     assert abs(sv.fidelity(ref) - 1) < 1e-12
 
 
-@pytest.mark.parametrize("tma", [0, 1])
+@pytest.mark.parametrize("tma", [0, 1, 4])
 @pytest.mark.parametrize("axes,glog", [(1, 0), (2, 1), (3, 0), (3, 3), (4, 0), (4, 2), (5, 0), (5, 3), (6, 0), (6, 1)])
 @pytest.mark.parametrize("n", [12, 15, 17])
 def test_batched_passes_on_many_axes_against_oracle(n, axes, glog, tma):
@@ -444,7 +444,8 @@ def test_batched_passes_on_many_axes_against_oracle(n, axes, glog, tma):
     dev = _sv(psi, n + 1, fusion=2, strict=False, batch=8)
     dev.set_option(_lib.OPT_BATCH_AXES, axes)
     dev.set_option(_lib.OPT_CHUNK_LOG2, glog)
-    dev.set_option(_lib.OPT_TMA, tma)     # 1: tiles staged by bulk copies (k_fused_tma); 0: register-staged kernels
+    dev.set_option(_lib.OPT_TMA, 1 if tma == 1 else 0)     # 1: tiles staged by bulk copies (k_fused_tma); else register-staged
+    dev.set_option(_lib.OPT_TILE_REGS, 4 if tma == 4 else 3)   # 4: 2^4 amplitudes per thread in k_fused_tile
     orc = OracleStatevector(psi, max_qubits=n + 1)
     npass0 = dev.stats()["fused"]["launches"]
     for step in range(48):

@@ -35,6 +35,7 @@ def main():
 
     def run(label, axes, stages, batch_axes, glog, tma=int(os.environ.get("MB_TMA", "1"))):
         sv.set_option(_lib.OPT_TMA, tma)
+        sv.set_option(_lib.OPT_TILE_REGS, int(os.environ.get("MB_TILE_REGS", "4")))
         sv.set_option(_lib.OPT_BATCH_AXES, batch_axes)
         sv.set_option(_lib.OPT_CHUNK_LOG2, glog)
         sv.set_option(_lib.OPT_BATCH, min(8, stages))
