@@ -358,7 +358,7 @@ def free_device_memory() -> None:
     torch.cuda.empty_cache()
 
 
-def make_gpu_backend(world: int, width: int, selector, *, fusion=2, nonstrict=True, batch=8, device=0, pattern=None,
+def make_gpu_backend(world: int, width: int, selector, *, fusion=2, nonstrict=True, batch=12, device=0, pattern=None,
                      schedule=True):
     from graphix_b200 import B200StatevectorBackend
 
@@ -366,7 +366,8 @@ def make_gpu_backend(world: int, width: int, selector, *, fusion=2, nonstrict=Tr
         from graphix_b200.sharded import ShardedStatevectorBackend
 
         return ShardedStatevectorBackend.with_capacity(width, branch_selector=selector, fusion=fusion,
-                                                       strict=not nonstrict, pattern=pattern if schedule else None)
+                                                       strict=not nonstrict, batch=batch or 12,
+                                                       pattern=pattern if schedule else None)
     lazy = fusion == 2 and nonstrict
     return B200StatevectorBackend.with_capacity(width, branch_selector=selector, fusion=fusion, device=device,
                                                 strict=not lazy, batch=batch if lazy else 0)
@@ -589,7 +590,7 @@ def gpu_arm(args) -> None:
                 random_sel = rec
             elif label == "random_selector_batched":
                 rec["selector"] = "RandomBranchSelector(pr_calc=True), rng=default_rng(0)"
-                rec["note"] = "same selector in the bench-default mode (strict=False, batch=8)"
+                rec["note"] = "same selector in the bench-default mode (strict=False, batch=12)"
                 random_sel_b = rec
             else:
                 per_command = rec
@@ -702,7 +703,7 @@ def gpu_arm(args) -> None:
                    "selector": "ConstBranchSelector(0)" if args.selector != "random" else "RandomBranchSelector(pr_calc=True), rng=default_rng(0)",
                    "fusion": args.fusion, "max_commands": args.max_commands or None,
                    "strict_norm_check": not args.nonstrict, "batch": args.batch if args.nonstrict else 0,
-                   "mode": "lazy N/E->M fusion, non-blocking batched projections (opt-in: strict=False, batch=8); the "
+                   "mode": "lazy N/E->M fusion, non-blocking batched projections (opt-in: strict=False, batch=12); the "
                            "library default (strict) is reported as `strict_lazy`" if args.nonstrict and args.fusion == 2 else "as flagged",
                    "parallelism": f"shard{world}" if world > 1 else "single",
                    "l2": "state >> 126 MB L2: inputs larger than L2, no flush needed"},
@@ -950,7 +951,7 @@ def main() -> None:
                     help="const0 = ConstBranchSelector(0) (BASELINE configs); random = graphix's default selector")
     ap.add_argument("--no-schedule", action="store_true",
                     help="N > 1: do not hand the pattern's measurement order to the sharded backend (eviction heuristic only)")
-    ap.add_argument("--batch", type=int, default=8, help="N = 1, non-strict: fused projections per pass (0 = one pass each)")
+    ap.add_argument("--batch", type=int, default=12, help="non-strict: fused projections per pass, up to 12 (0 = one pass each)")
     ap.set_defaults(nonstrict=True)
     ap.add_argument("--cpu-window", type=int, default=0, help="commands per CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -31,7 +31,7 @@ constexpr int TILE_BITS = 11;   // k_contract<4,true>: a CTA tile spans the lowe
 constexpr int U_DEF = 4;
 constexpr int RING = 4096;    // result slots (256 B each, pinned + mapped)
 constexpr int GXSV_VERSION = 100;
-constexpr int MAX_BATCH_AXES = 6;  // distinct physical bits one batched pass may act on (GXSV_BATCH_AXES = 1..7).
+constexpr int MAX_BATCH_AXES = 7;  // distinct physical bits one batched pass may act on (GXSV_BATCH_AXES = 1..7).
 // Up to 3 axes run in k_fused_batch (2^3 amplitudes per thread in registers, 4 CTAs per SM); 4..6 axes run in
 // k_fused_tile, which keeps three axes at a time in registers and transposes the CTA tile through shared memory
 // between phases.  (Round 1 measured a 4-axis all-register pass: 128 registers, 2 CTAs per SM, 0.64 of the copy rate.)

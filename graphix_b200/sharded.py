@@ -46,7 +46,7 @@ _X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
 class GpuShardEngine:
     """The local shard: a ``B200Statevector`` in distributed mode plus torch staging buffers."""
 
-    def __init__(self, local_bits: int, device: int | None = None, strict: bool = True, batch: int = 8) -> None:
+    def __init__(self, local_bits: int, device: int | None = None, strict: bool = True, batch: int = 12) -> None:
         self.sv = B200Statevector(nqubit=0, max_qubits=local_bits, device=device, fusion=2, strict=strict,
                                   batch=0 if strict else batch)
         self.sv.set_option(_lib.OPT_DIST, 1)
@@ -189,7 +189,8 @@ class ShardedStatevector:
     CHUNK_MIN = 1 << 25   # amplitudes per staging buffer: at least 512 MiB (measured: 128 MiB chunks halve the exchange
     # rate — every torch.distributed P2P batch has a fixed cost of a few hundred microseconds on both sides) ...
     CHUNK_MAX = 1 << 27   # ... at most 2 GiB; two send + two receive buffers, allocated on demand
-    WINDOW = 64      # non-strict mode: projections between two renormalisations (one small all-reduce each)
+    WINDOW = 256     # non-strict mode: projections between two renormalisations (one small all-reduce each; the stored
+    # amplitudes grow by at most a factor 2 per projection in between: 2^256 is far inside the double range)
 
     def __init__(self, engine, group=None, strict: bool | None = None) -> None:
         self.engine = engine
@@ -918,7 +919,8 @@ class ShardedStatevectorBackend(B200StatevectorBackend):
 
     @classmethod
     def with_capacity(cls, max_qubits: int, state=None, *, engine=None, group=None, device: int | None = None,
-                      fusion: int = 2, strict: bool = True, pattern=None, **kwargs) -> "ShardedStatevectorBackend":
+                      fusion: int = 2, strict: bool = True, pattern=None, batch: int = 12,
+                      **kwargs) -> "ShardedStatevectorBackend":
         """``max_qubits`` is the TOTAL width (``Pattern.max_space()``); each rank holds ``max_qubits - log2 P`` bits.
 
         ``pattern`` (optional, like ``TensorNetworkBackend(pattern, ...)``, graphix/sim/tensornet.py:617-674): the
@@ -928,7 +930,7 @@ class ShardedStatevectorBackend(B200StatevectorBackend):
         P = dist.get_world_size(group) if dist.is_initialized() else 1
         g = P.bit_length() - 1
         if engine is None:
-            engine = GpuShardEngine(max(max_qubits - g, 1), device=device, strict=strict)
+            engine = GpuShardEngine(max(max_qubits - g, 1), device=device, strict=strict, batch=batch)
         backend = cls(ShardedStatevector(engine, group=group, strict=strict), **kwargs)
         if pattern is not None:
             backend.use_schedule(pattern)

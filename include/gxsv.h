@@ -56,7 +56,7 @@ enum {
   GXSV_OPT_DIST = 4,    /* 1 = this handle is one shard of a distributed state (see the sharded section) */
   GXSV_OPT_BATCH = 5,   /* K > 0 (needs FUSION = 2, STRICT = 0): queue up to K fused projections and execute them in
                          * ONE pass over the register; zero-norm errors surface at gxsv_sync / gxsv_flatten */
-  GXSV_OPT_BATCH_AXES = 6, /* tuning: distinct physical bits one batched pass may act on (1..6, default 6) */
+  GXSV_OPT_BATCH_AXES = 6, /* tuning: distinct physical bits one batched pass may act on (1..7, default 7) */
   GXSV_OPT_CHUNK_LOG2 = 7, /* tuning: log2 of the consecutive blocks / tiles a CTA of a batched pass takes at a time */
   GXSV_OPT_TMA = 8,        /* 1 = batched passes stage CTA tiles through shared memory with bulk copies (cp.async.bulk +
                             * mbarrier) whenever the layout allows; 0 (default) = register-staged kernels */
