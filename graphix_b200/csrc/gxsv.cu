@@ -2039,19 +2039,23 @@ int gxsv_swap_peer(gxsv_t* h, int q, int slot, int my_bit, double fre, double fi
   static const int dbg_mode = std::getenv("GXSV_SWAP_MODE") ? std::atoi(std::getenv("GXSV_SWAP_MODE")) : 0;
   static const int dbg_u = std::getenv("GXSV_SWAP_U") ? std::atoi(std::getenv("GXSV_SWAP_U")) : U_DEF;
   static const int dbg_ctas = std::getenv("GXSV_SWAP_CTAS") ? std::atoi(std::getenv("GXSV_SWAP_CTAS")) : 8;
+  static const int blocked = std::getenv("GXSV_SWAP_BLOCKED") ? std::atoi(std::getenv("GXSV_SWAP_BLOCKED")) : 1;
   {
     Launch L(h, GXSV_K_MISC, 64.0 * (double)count);
     const int u = (dbg_u == 8 || dbg_u == 2 || dbg_u == 1) ? dbg_u : U_DEF;
     uint64_t blocks = (count + (uint64_t)TPB * u - 1) / ((uint64_t)TPB * u);
     blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)h->sm_count * std::max(1, dbg_ctas)));
+    // contiguous range per CTA, a multiple of the per-iteration chunk
+    const uint64_t cpi = (uint64_t)TPB * u;
+    const uint64_t span = blocked ? ((count + blocks - 1) / blocks + cpi - 1) / cpi * cpi : 0;
     if (u == 8)
-      k_swap_peer<8><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode);
+      k_swap_peer<8><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode, span);
     else if (u == 2)
-      k_swap_peer<2><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode);
+      k_swap_peer<2><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode, span);
     else if (u == 1)
-      k_swap_peer<1><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode);
+      k_swap_peer<1><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode, span);
     else
-      k_swap_peer<U_DEF><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode);
+      k_swap_peer<U_DEF><<<(int)blocks, TPB, 0, h->stream>>>(h->psi, h->peer_psi[slot], hs, my_or, peer_or, first, count, d2(f), d2(finv), scale, dbg_mode, span);
   }
   return check_launch(h, "k_swap_peer");
 }

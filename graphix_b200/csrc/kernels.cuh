@@ -1239,17 +1239,22 @@ __global__ void __launch_bounds__(TPB) k_swap_peer(double2* __restrict__ mine, d
                                                    const __grid_constant__ Holes hs, const uint64_t my_or,
                                                    const uint64_t peer_or, const uint64_t first, const uint64_t count,
                                                    const double2 f_mine, const double2 f_peer, const int scale,
-                                                   const int mode) {
-  // mode 0 = swap; 1 / 2 = diagnostics only (tools/microbench_swap.py): pull (mine <- peer) / push (peer <- mine)
+                                                   const int mode, const uint64_t span) {
+  // mode 0 = swap; 1 / 2 = diagnostics only (tools/microbench_swap.py): pull (mine <- peer) / push (peer <- mine).
+  // span > 0: every CTA walks ONE contiguous range of `span` elements (it stays inside the same 2 MB pages of the local
+  // and of the peer mapping for many iterations); span = 0: plain grid stride.
   const uint64_t chunk = (uint64_t)TPB * U;
-  for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < count; base += (uint64_t)gridDim.x * chunk) {
+  const uint64_t lo = span ? (uint64_t)blockIdx.x * span : (uint64_t)blockIdx.x * chunk;
+  const uint64_t hi = span ? (lo + span < count ? lo + span : count) : count;
+  const uint64_t step = span ? chunk : (uint64_t)gridDim.x * chunk;
+  for (uint64_t base = lo; base < hi; base += step) {
     double2 a[U], b[U];
     uint64_t e[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
       e[u] = expand(first + k, hs);
-      if (k < count) {
+      if (k < hi) {
         if (mode != 2) b[u] = ld_amp(peer + (e[u] | peer_or));      // NVLink load
         if (mode != 1) a[u] = ld_amp(mine + (e[u] | my_or));
       }
@@ -1257,7 +1262,7 @@ __global__ void __launch_bounds__(TPB) k_swap_peer(double2* __restrict__ mine, d
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint64_t k = base + (uint64_t)u * TPB + threadIdx.x;
-      if (k < count) {
+      if (k < hi) {
         if (mode != 1) st_amp(peer + (e[u] | peer_or), scale ? cmul(f_peer, a[u]) : a[u]);   // NVLink store
         if (mode != 2) st_amp(mine + (e[u] | my_or), scale ? cmul(f_mine, b[u]) : b[u]);
       }
