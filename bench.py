@@ -51,16 +51,18 @@ def measured_peak() -> tuple[float, str]:
 
 
 # kernel kind (gxsv_stats) -> kernel name in the committed ncu captures
-_NCU_KERNEL = {"fused": "k_fused_batch", "contract": "k_contract", "fill": "k_fill", "cz": "k_cz_star"}
+_NCU_KERNEL = {"fused": "k_fused_tile", "contract": "k_contract", "fill": "k_fill", "cz": "k_cz_star"}
 
 
 def ncu_traffic(kind: str, workload: str, batched: bool) -> float | None:
     """DRAM bytes per launch of the dominant kernel from the ncu --set full capture committed under profiles/
-    (taken on config 2; not transferable to other workloads, hence None there)."""
+    (taken on config 2; not transferable to other workloads, hence None there).  A constant read from the committed
+    capture, not measured in this run: it goes stale when the kernel changes (profiles/r02_ncu_traffic.json says which
+    capture each number comes from)."""
     if workload != "config2_rand26x20":
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             t = json.load(f)
         name = _NCU_KERNEL.get(kind)
         if kind == "fused" and not batched:

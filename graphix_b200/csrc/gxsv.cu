@@ -285,6 +285,8 @@ unsigned long long parity_table(uint64_t mask, const unsigned char* regbit, int 
 // phases (out may be NULL: the queueing code only asks whether one more stage still fits MAX_PHASES).  With `out`,
 // also tabulates the offsets the kernel addresses with.
 int plan_phases(const Batch& bt, TileBatch* out, int R) {
+  // XOR swizzle of a shared-memory slot index (see k_fused_tile): bit 2 ^= parity of the bits above it
+  auto sw = [](unsigned int x) { return x ^ ((unsigned int)(__builtin_popcount(x >> 3) & 1) << 2); };
   int nph = 0;
   int i = 0;
   const int A = bt.naxes, F = (5 + R) - A;
@@ -320,11 +322,11 @@ int plan_phases(const Batch& bt, TileBatch* out, int R) {
         for (int k = 0; k < R; ++k)
           if ((b >> k) & 1) { go |= 1ull << regbit[k]; so |= 1u << T[k]; }
         out->gbits[nph][b] = go;
-        out->sbits[nph][b] = (unsigned short)(so << F);
+        out->sbits[nph][b] = (unsigned short)sw(so << F);
       }
       for (int k = 0; k < 4; ++k) {
         out->goth[nph][k] = (k < no) ? (1ull << bt.axbit[oth[k]]) : 0ull;
-        out->soth[nph][k] = (k < no) ? (unsigned short)((1u << oth[k]) << F) : (unsigned short)0;
+        out->soth[nph][k] = (k < no) ? (unsigned short)sw((1u << oth[k]) << F) : (unsigned short)0;
       }
       out->s_begin[nph] = (unsigned char)i;
       out->s_end[nph] = (unsigned char)j;

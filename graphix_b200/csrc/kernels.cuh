@@ -588,6 +588,11 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double2* tile = tile_all + ((size_t)warp << WT);
   const unsigned int f = lane & ((1u << F) - 1u);
+  // shared-memory slots are XOR-swizzled: bit 2 of the slot index ^= parity of the bits above it, so that the 8 lanes of
+  // a quarter warp (one 128-byte wavefront of 16-byte accesses) always hit 8 different bank groups — without it passes on
+  // 7 axes (F = 2) ran with 2-way conflicts on every transpose (ncu: 53 % of the shared wavefronts).  The swizzle is
+  // linear over XOR and the parts of an index occupy disjoint bits, so the host tabulates it per part.
+  const unsigned int fsw = f ^ ((__popc(f >> 3) & 1u) << 2);
   const int r = lane >> F;
   const double g = ctrl->g;
   const int nphases = bt.nphases;
@@ -606,10 +611,10 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
       // emulated addresses were all in range; the uniform form costs three predicated ORs)
       auto lane_off = [&](int p, uint64_t& go, unsigned int& so) {
         go = base;
-        so = f;
+        so = fsw;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
-          if ((r >> i) & 1) { go |= bt.goth[p][i]; so |= bt.soth[p][i]; }
+          if ((r >> i) & 1) { go |= bt.goth[p][i]; so ^= bt.soth[p][i]; }
       };
       uint64_t gthread;
       unsigned int sthread;
@@ -642,10 +647,10 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
           const unsigned int s_new = sthread;
           __syncwarp();                             // every lane has read its slots of the previous transpose
 #pragma unroll
-          for (int b = 0; b < D; ++b) tile[s_old | bt.sbits[p][b]] = v[b];
+          for (int b = 0; b < D; ++b) tile[s_old ^ bt.sbits[p][b]] = v[b];
           __syncwarp();
 #pragma unroll
-          for (int b = 0; b < D; ++b) v[b] = tile[s_new | bt.sbits[p + 1][b]];
+          for (int b = 0; b < D; ++b) v[b] = tile[s_new ^ bt.sbits[p + 1][b]];
         } else {
           double2* dst = psi + gthread;
 #pragma unroll
