@@ -371,8 +371,9 @@ def make_gpu_backend(world: int, width: int, selector, *, fusion=2, nonstrict=Tr
                                                        strict=not nonstrict, batch=batch or 12,
                                                        pattern=pattern if schedule else None)
     lazy = fusion == 2 and nonstrict
+    # strict + batch > 0 is the library default: only projections whose outcome probability is analytic are queued
     return B200StatevectorBackend.with_capacity(width, branch_selector=selector, fusion=fusion, device=device,
-                                                strict=not lazy, batch=batch if lazy else 0)
+                                                strict=not lazy, batch=batch if fusion == 2 else 0)
 
 
 def sharded_parity(world: int) -> dict:
@@ -428,16 +429,18 @@ def config3_record(args, timer: Timer, local_rank: int) -> dict:
                       "projections_per_pass": sum(1 for c in pattern if c.kind.name == "M") * 2 / max(stats["fused"]["launches"], 1)}
     del b
     free_device_memory()
-    # strict lazy mode (reference error timing: every projection waits for its norm): a bounded prefix window
+    # strict mode (reference error timing) on a bounded prefix window: the library default (analytic projections share
+    # passes) and batch = 0 (one k_fused pass per projection, every measure() waits for its norm)
     nwin = 2400
     sub = mbqc.Pattern(pattern.input_nodes, list(pattern)[:nwin])
-    b = make_gpu_backend(1, width, sel, device=local_rank, nonstrict=False)
-    ms, stats = timed_pattern(timer, b, sub, 2, 1)
-    out["strict_lazy"] = {"value": nwin * 2 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 2, "steps": 2, "warmup": 1,
-                          "window": f"first {nwin} commands", "roofline": roofline_of(stats, ms),
-                          "kernels": kernel_table(stats, 2, measured_peak()[0])}
-    del b
-    free_device_memory()
+    for label, bt in (("strict_lazy", args.batch), ("strict_unbatched", 0)):
+        b = make_gpu_backend(1, width, sel, device=local_rank, nonstrict=False, batch=bt)
+        ms, stats = timed_pattern(timer, b, sub, 2, 1)
+        out[label] = {"value": nwin * 2 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 2, "steps": 2, "warmup": 1,
+                      "batch": bt, "window": f"first {nwin} commands", "roofline": roofline_of(stats, ms),
+                      "kernels": kernel_table(stats, 2, measured_peak()[0])}
+        del b
+        free_device_memory()
     if not args.no_cpu:
         n_cmds = 8
         times, kind, cores, note = host_window(name, pattern, n_cmds, 1, 0, force_port=args.port)
@@ -567,23 +570,30 @@ def gpu_arm(args) -> None:
     #   strict_lazy : fusion = 2, strict — the library default: lazy N/E->M fusion, every projection waits for its
     #                 norm (reference error timing); `value` itself is fusion = 2, non-strict, batched
     #   random_selector : RandomBranchSelector(pr_calc=True), graphix's default — a probability query per measurement
-    per_command = strict_lazy = random_sel = random_sel_b = None
+    per_command = strict_lazy = strict_unb = random_sel = random_sel_b = None
     peak = measured_peak()[0]
     if world == 1 and args.fusion == 2 and args.nonstrict and not args.no_per_command and args.selector != "random":
-        for label, kw, sel2, rk in (("strict_lazy", {"nonstrict": False}, selector, lambda: {}),
-                                    ("random_selector", {"nonstrict": False}, mbqc.RandomBranchSelector(pr_calc=True),
-                                     lambda: {"rng": np.random.default_rng(0)}),
+        for label, kw, sel2, rk in (("strict_lazy", {"nonstrict": False, "batch": args.batch}, selector, lambda: {}),
+                                    ("strict_unbatched", {"nonstrict": False, "batch": 0}, selector, lambda: {}),
+                                    ("random_selector", {"nonstrict": False, "batch": args.batch},
+                                     mbqc.RandomBranchSelector(pr_calc=True), lambda: {"rng": np.random.default_rng(0)}),
                                     ("random_selector_batched", {"batch": args.batch}, mbqc.RandomBranchSelector(pr_calc=True),
                                      lambda: {"rng": np.random.default_rng(0)}),
                                     ("per_command", {"fusion": 1}, selector, lambda: {})):
             b2 = make_gpu_backend(1, width, sel2, device=local_rank, **kw)
             nst = max(2, args.steps - 2) if label != "strict_lazy" else args.steps
             ms2, st2 = timed_pattern(timer, b2, pattern, nst, 2, rk)
-            rec = {"fusion": kw.get("fusion", 2), "strict": "batch" not in kw, "value": ncmd * nst / (ms2 * 1e-3), "unit": UNIT,
+            rec = {"fusion": kw.get("fusion", 2), "strict": "nonstrict" in kw or "fusion" in kw,
+                   "batch": kw.get("batch", 0 if "fusion" in kw else args.batch),
+                   "value": ncmd * nst / (ms2 * 1e-3), "unit": UNIT,
                    "ms_per_step": ms2 / nst, "steps": nst, "warmup": 2, "kernels": kernel_table(st2, nst, peak)}
             if label == "strict_lazy":
-                rec["note"] = "library default (B200StatevectorBackend()): zero-norm RuntimeError raised by measure() itself"
+                rec["note"] = ("library default (B200StatevectorBackend()): zero-norm RuntimeError raised by measure() itself; "
+                               "projections whose outcome probability is analytically 1/2 cannot fail and share passes")
                 strict_lazy = rec
+            elif label == "strict_unbatched":
+                rec["note"] = "strict, batch=0: one k_fused pass per projection, every measure() waits for its norm"
+                strict_unb = rec
             elif label == "random_selector":
                 rec["selector"] = "RandomBranchSelector(pr_calc=True), rng=default_rng(0) (graphix's default selector)"
                 rec["note"] = ("everything at its default: strict library mode + graphix's default selector; the probability "
@@ -714,7 +724,8 @@ def gpu_arm(args) -> None:
         "kernels": kernel_table(stats, args.steps, peak),
         "projections_per_pass": (sum(1 for c in pattern if c.kind.name == "M") * args.steps / stats["fused"]["launches"])
         if stats.get("fused", {}).get("launches") else None,
-        "per_command": per_command, "strict_lazy": strict_lazy, "random_selector": random_sel,
+        "per_command": per_command, "strict_lazy": strict_lazy, "strict_unbatched": strict_unb,
+        "random_selector": random_sel,
         "random_selector_batched": random_sel_b,
     }
     if world > 1:

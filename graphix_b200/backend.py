@@ -93,7 +93,7 @@ class B200StatevectorBackend(_Base):  # type: ignore[misc, valid-type]
 
     def __init__(self, state: B200Statevector | None = None, *, node_index=None, branch_selector=None,
                  symbolic: bool = False, device: int | None = None, fusion: int = 2, strict: bool = True,
-                 batch: int = 0) -> None:
+                 batch: int | None = None) -> None:
         if symbolic:
             raise ValueError(
                 "Statevector backend does not support `symbolic` simulation. Consider using backend in `graphix-symbolic` plugin."
@@ -118,7 +118,7 @@ class B200StatevectorBackend(_Base):  # type: ignore[misc, valid-type]
         dev = kwargs.pop("device", None)
         fusion = kwargs.pop("fusion", 2)
         strict = kwargs.pop("strict", True)
-        batch = kwargs.pop("batch", 0)
+        batch = kwargs.pop("batch", None)
         if state is None:
             st = B200Statevector(nqubit=0, max_qubits=max_qubits, device=dev, fusion=fusion, strict=strict, batch=batch)
         else:

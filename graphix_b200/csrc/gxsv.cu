@@ -1464,8 +1464,22 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
       } else {
         const int p = h->q[q].phys;
         const cplx s0 = h->q[vi].s0, s1 = h->q[vi].s1;
-        if (h->batch_max > 0 && !h->strict) {
-          // non-strict: queue the butterfly; up to batch_max stages on <= MAX_BATCH_AXES distinct bits run as one pass
+        // |+> / |-> partners (s1 = +-s0): take the scalar f = s0 * c_pivot out of the stage (Stage kinds 0 / 1 in
+        // kernels.cuh).  Its phase (sharded: f itself, so that the all-reduced norms stay those of the true state)
+        // stays in the host scalar, |f|^2 goes into the published norms.  A sharded state may carry a rank-dependent
+        // sign on c1, and the host scalar must be rank uniform: there only c0 is ever taken out.
+        const bool same = (s1 == s0), opp = (s1 == -s0);
+        const int pivot = (std::abs(c0) >= std::abs(c1)) ? 0 : 1;
+        const bool fast = (same || opp) && std::abs(s0) > 0.0 && !(h->dist && pivot == 1);
+        const cplx a_ratio = fast ? (pivot ? c0 / c1 : c1 / c0) : cplx(0.0);
+        // |a| = 1 (XY-plane measurement, |+> / |-> partner): the outcome probability is 1/2 whatever the state, i.e.
+        // |row . psi|^2 = 2 |s0|^2 |row_pivot|^2 |psi|^2 — known without looking at the register
+        const bool analytic = fast && h->analytic_norms && std::abs(std::norm(a_ratio) - 1.0) <= 1e-12;
+        // Queue the butterfly (up to batch_max stages on up to batch_axes distinct bits run as ONE pass) in non-strict
+        // mode always, and in STRICT mode whenever the outcome probability is analytic: such a projection cannot be the
+        // zero-norm branch the reference raises for (statevec.py:1192-1193), and the half the reference keeps is known,
+        // so nothing about it has to be waited for — error timing and results stay exactly the reference's.
+        if (h->batch_max > 0 && (!h->strict || (analytic && !h->dist))) {
           int ax = -1;
           for (int a = 0; a < h->batch.naxes; ++a) if (h->batch.axbit[a] == p) ax = a;
           // more than three axes need a CTA tile of 2^11 amplitudes (k_fused_tile)
@@ -1488,30 +1502,22 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           Stage& st = h->batch.st[h->batch.nstages++];
           st.m00 = d2(s0 * c0); st.m01 = d2(s0 * c1); st.m10 = d2(s1 * c0); st.m11 = d2(-s1 * c1);
           st.mq = mq; st.mv = mv; st.axis = ax; st.qtab = st.vtab = 0; st.pad = 0;
-          // |+> / |-> partners (s1 = +-s0): take the scalar f = s0 * c_pivot out of the stage (Stage kinds 0 / 1 in
-          // kernels.cuh).  Its phase (sharded: f itself, so that the all-reduced norms stay those of the true state)
-          // stays in the host scalar, |f|^2 goes into the published norms.  A sharded state may carry a rank-dependent
-          // sign on c1, and the host scalar must be rank uniform: there only c0 is ever taken out.
-          const bool same = (s1 == s0), opp = (s1 == -s0);
-          const int pivot = (std::abs(c0) >= std::abs(c1)) ? 0 : 1;
-          const bool fast = (same || opp) && std::abs(s0) > 0.0 && !(h->dist && pivot == 1);
           cplx f = 1.0;
           st.kind = 2;
           st.neg = 0;
           st.a = d2(0.0);
           if (fast) {
             f = s0 * (pivot ? c1 : c0);
-            st.a = d2(pivot ? c0 / c1 : c1 / c0);
+            st.a = d2(a_ratio);
             st.kind = (unsigned char)pivot;
             st.neg = opp ? 1 : 0;
           }
           const int k = h->batch.nstages - 1;
           h->batch.nscale[k] = ((k > 0 && !h->dist) ? h->batch.nscale[k - 1] : 1.0) * std::norm(f);
-          // |a| = 1 (XY-plane measurement, |+> / |-> partner): the outcome probability is 1/2 whatever the state, i.e.
-          // |row . psi|^2 = 2 |s0|^2 |row_pivot|^2 |psi|^2 — no need to accumulate the norm of this stage
+          // analytic probability: no need to accumulate the norm of this stage
           st.acc = 1;
           double an = 0.0;
-          if (fast && std::abs(std::norm(cplx(st.a.x, st.a.y)) - 1.0) <= 1e-12 && h->analytic_norms) {
+          if (analytic) {
             const cplx mp = big ? (pivot ? m11 : m10) : (pivot ? m01 : m00);
             an = 2.0 * std::norm(s0) * std::norm(mp);
             st.acc = 0;

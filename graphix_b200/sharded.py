@@ -48,7 +48,7 @@ class GpuShardEngine:
 
     def __init__(self, local_bits: int, device: int | None = None, strict: bool = True, batch: int = 12) -> None:
         self.sv = B200Statevector(nqubit=0, max_qubits=local_bits, device=device, fusion=2, strict=strict,
-                                  batch=0 if strict else batch)
+                                  batch=0 if strict else batch)   # strict sharded projections wait for the all-reduced norm
         self.sv.set_option(_lib.OPT_DIST, 1)
         # what was really allocated: the constructor may have fallen back to half the requested register (lazy fusion
         # rarely needs the last qubit); qubits beyond it go to free rank bits instead of failing later

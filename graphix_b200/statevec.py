@@ -93,13 +93,15 @@ class B200Statevector:
     ``max_qubits`` preallocates capacity (``Pattern.max_space()``).
     Extra keyword-only parameters: ``device`` (CUDA ordinal), ``fusion``
     (0 = one kernel per command, 1 = runs of E fused, 2 = lazy N/E->M fusion [default]),
-    ``strict`` (wait for every projection norm, default True; with ``strict=False`` the zero-norm
-    ``RuntimeError`` surfaces at ``sync()`` / ``flatten()`` / ``finalize``), ``batch`` (K > 0 with
-    ``strict=False``: up to K consecutive fused projections run as ONE pass over the register).
+    ``strict`` (default True: the zero-norm ``RuntimeError`` is raised by the projection itself, like the reference;
+    with ``strict=False`` it surfaces at ``sync()`` / ``flatten()`` / ``finalize``), ``batch`` (default 12 with
+    ``fusion=2``: up to K consecutive fused projections run as ONE pass over the register — with ``strict=True`` only
+    those whose outcome probability is known analytically, i.e. that cannot be a zero-norm branch; everything else
+    still waits for its norm).
     """
 
     def __init__(self, data=BasicStates.PLUS, nqubit: int | None = None, max_qubits: int | None = None, *,
-                 device: int | None = None, fusion: int = 2, strict: bool = True, batch: int = 0) -> None:
+                 device: int | None = None, fusion: int = 2, strict: bool = True, batch: int | None = None) -> None:
         if nqubit is not None and nqubit < 0:
             raise ValueError("`nqubit` must be a non-negative integer.")
         if max_qubits is not None and max_qubits < 0:
@@ -130,9 +132,11 @@ class B200Statevector:
             _lib.raise_for(self._lib, None, rc)
         self._check(self._lib.gxsv_set_option(self._h, _lib.OPT_FUSION, int(fusion)))
         self._check(self._lib.gxsv_set_option(self._h, _lib.OPT_STRICT, int(bool(strict))))
+        if batch is None:
+            batch = 12 if fusion == 2 else 0
         if batch:
-            if strict or fusion != 2:
-                raise ValueError("`batch` needs fusion=2 and strict=False")
+            if fusion != 2:
+                raise ValueError("`batch` needs fusion=2")
             self._check(self._lib.gxsv_set_option(self._h, _lib.OPT_BATCH, int(batch)))
         if vec is not None:
             self._add(vec, n)

@@ -59,12 +59,12 @@ def test_batched_projections_share_passes_and_defer_errors():
     # |0> measured along Z with outcome 1: probability 0.  strict raises in measure, non-strict at finalize.
     p = mbqc.Pattern([], [mbqc.N(0, mbqc.BasicStates.ZERO), mbqc.N(1), mbqc.E((0, 1)), mbqc.N(2), mbqc.E((1, 2)),
                           mbqc.M(0, mbqc.Measurement.Z), mbqc.M(1, mbqc.Measurement.XY(0.3))])
-    for kw in ({"strict": True}, {"strict": False}, {"strict": False, "batch": 4}):
+    for kw in ({"strict": True}, {"strict": True, "batch": 0}, {"strict": False}, {"strict": False, "batch": 4}):
         b = B200StatevectorBackend.with_capacity(3, branch_selector=mbqc.ConstBranchSelector(1), **kw)
         with pytest.raises(RuntimeError):
             PatternSimulator(p, b).run()
     with pytest.raises(ValueError):
-        B200StatevectorBackend.with_capacity(3, batch=4)   # batching needs strict=False
+        B200StatevectorBackend.with_capacity(3, fusion=1, batch=4)   # batching needs the lazy mode (fusion=2)
 
 
 @pytest.mark.parametrize("fusion", [1, 2])
@@ -127,3 +127,31 @@ def test_noise_not_supported():
     b = B200StatevectorBackend()
     with pytest.raises(NoiseNotSupportedError):
         b.apply_noise(None)
+
+
+def test_strict_mode_batches_analytic_projections_and_keeps_reference_error_timing():
+    """Library default (strict=True, batch=12): projections whose outcome probability is analytically 1/2 (XY-plane
+    measurement of a qubit entangled with a fresh |+>) are queued and share passes; a projection that CAN fail is waited
+    for, so the zero-norm RuntimeError is still raised by the very `measure` call the reference raises it in."""
+    d = load_golden("rand14x4")
+    pattern = pattern_from_dict(d)
+    trace = d["traces"][0]
+    sel = mbqc.FixedBranchSelector({int(k): v for k, v in trace["outcomes"].items()})
+    b = B200StatevectorBackend.with_capacity(pattern.max_space(), branch_selector=sel)         # all defaults
+    PatternSimulator(pattern, b).run()
+    n_meas = sum(1 for c in pattern if c.kind.name == "M")
+    assert b.state.stats()["fused"]["launches"] * 2 < n_meas           # several projections per pass, in strict mode
+    ref = np.asarray(trace["final_state"], dtype=np.float64).view(np.complex128)
+    assert abs(np.vdot(ref, b.state.flatten())) ** 2 >= 1 - F_TOL
+    # a chain of analytic projections, then |0> measured along Z with outcome 1 (probability 0), then more commands
+    cmds = [mbqc.N(0)]
+    for i in range(1, 7):
+        cmds += [mbqc.N(i), mbqc.E((i - 1, i)), mbqc.M(i - 1, mbqc.Measurement.XY(0.1 * i))]
+    cmds += [mbqc.N(7, mbqc.BasicStates.ZERO), mbqc.N(8), mbqc.E((7, 8)), mbqc.M(7, mbqc.Measurement.Z),
+             mbqc.N(9), mbqc.E((8, 9)), mbqc.M(8, mbqc.Measurement.XY(0.3))]
+    p = mbqc.Pattern([], cmds)
+    b = B200StatevectorBackend.with_capacity(4, branch_selector=mbqc.ConstBranchSelector(1))
+    sim = PatternSimulator(p, b)
+    with pytest.raises(RuntimeError):
+        sim.run()
+    assert sorted(sim.measure_method.results) == [0, 1, 2, 3, 4, 5]     # raised by measure(7), not at finalize
