@@ -68,10 +68,15 @@ def test_batched_projections_share_passes_and_defer_errors():
 
 
 @pytest.mark.parametrize("fusion", [1, 2])
-@pytest.mark.parametrize("name", ["config1_rand8x5", "qaoa7", "rand11x6"])
+@pytest.mark.parametrize("name", ["config1_rand8x5", "qaoa7", "rand11x6", "rand20x5", "nonflow22"])
 def test_random_branch_same_rng_as_oracle(name, fusion):
     """RandomBranchSelector(pr_calc=True) with the same seed must take the same branch on both backends
-    (probabilities agree to 1e-10, so `rng.random() > p0` agrees) and end in the same state."""
+    (probabilities agree to 1e-10, so `rng.random() > p0` agrees) and end in the same state.  `rand20x5` (21 live
+    qubits, 680 commands) is a flow pattern: nearly every probability is answered analytically (1/2, no pass) and the
+    projections share passes in the default strict mode; `nonflow22` has data-dependent probabilities (0.009 .. 0.865)
+    that need the reduction pass."""
+    if fusion == 1 and name in ("rand20x5", "nonflow22"):
+        pytest.skip("large cases run in the default (lazy) mode only")
     d = load_golden(name)
     pattern = pattern_from_dict(d)
     out = []
