@@ -71,6 +71,23 @@ def _fullsize_digests():
         return json.load(f)
 
 
+_PROBES: dict = {}
+
+
+def _probe(seed: int, n: int):
+    """The seeded Gaussian probe vectors (1 GiB each at 26 qubits) are generated once for all six cases."""
+    if (seed, n) not in _PROBES:
+        import sys
+
+        from helpers import GOLDEN
+
+        sys.path.insert(0, GOLDEN)
+        from make_fullsize_golden import probe_vector
+
+        _PROBES[(seed, n)] = probe_vector(seed, n)
+    return _PROBES[(seed, n)]
+
+
 @pytest.mark.parametrize("mode", ["per_command", "strict_lazy", "batched"])
 @pytest.mark.parametrize("run", ["const0", "seeded5"])
 def test_config2_against_reference_digests(run, mode):
@@ -79,7 +96,7 @@ def test_config2_against_reference_digests(run, mode):
     from helpers import GOLDEN
 
     sys.path.insert(0, GOLDEN)
-    from make_fullsize_golden import probe_vector, sample_indices
+    from make_fullsize_golden import sample_indices
 
     dig = _fullsize_digests()["runs"][run]
     pattern = pattern_from_dict(load_golden("config2_rand26x20"))
@@ -99,6 +116,6 @@ def test_config2_against_reference_digests(run, mode):
     phase = (ref_s[k] / got_s[k]) / abs(ref_s[k] / got_s[k])
     assert np.max(np.abs(got_s * phase - ref_s)) < 1e-12
     for seed, (re, im) in zip(_fullsize_digests()["probe_seeds"], dig["inner"]):
-        z = np.vdot(probe_vector(seed, n), flat) * phase
+        z = np.vdot(_probe(seed, n), flat) * phase
         assert abs(z - complex(re, im)) < 1e-9, (seed, z, re, im)       # |z| ~ 1: sum of 2^26 terms
     del flat, b
