@@ -439,31 +439,35 @@ __device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& 
     const unsigned int tq = (k < 4) ? (unsigned int)tq64 : (unsigned int)(tq64 >> 32);
     const unsigned int tv = (k < 4) ? (unsigned int)tv64 : (unsigned int)(tv64 >> 32);
     const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | ((k & 3) << 12)), sv = __byte_perm(tv, 0u, 0x0444 | ((k & 3) << 12));
-    double2 r0, r1;
+    // results are written straight into the slots they replace (fewer live temporaries: the unrolled stage variants
+    // then agree on where v[] lives and need no register moves where they join)
     if (KIND == 0) {
       double2 w = cmul(a, v[hi]);
       w.x = flip_sign(w.x, sq);
       w.y = flip_sign(w.y, sq);
-      r0 = make_double2(v[lo].x + w.x, v[lo].y + w.y);
-      r1 = make_double2(flip_sign(v[lo].x - w.x, sv), flip_sign(v[lo].y - w.y, sv));
+      v[hi].x = flip_sign(v[lo].x - w.x, sv);
+      v[hi].y = flip_sign(v[lo].y - w.y, sv);
+      v[lo].x += w.x;
+      v[lo].y += w.y;
     } else if (KIND == 1) {
       const double2 u = cmul(a, v[lo]);
-      const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
-      r0 = make_double2(u.x + t1.x, u.y + t1.y);
-      r1 = make_double2(flip_sign(u.x - t1.x, sv), flip_sign(u.y - t1.y, sv));
+      const double tx = flip_sign(v[hi].x, sq), ty = flip_sign(v[hi].y, sq);
+      v[hi].x = flip_sign(u.x - tx, sv);
+      v[hi].y = flip_sign(u.y - ty, sv);
+      v[lo].x = u.x + tx;
+      v[lo].y = u.y + ty;
     } else {
       const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
-      r0 = cmad2(st.m00, v[lo], st.m01, t1);
-      r1 = cmad2(st.m10, v[lo], st.m11, t1);
-      r1.x = flip_sign(r1.x, sv);
-      r1.y = flip_sign(r1.y, sv);
+      const double2 r0 = cmad2(st.m00, v[lo], st.m01, t1);
+      double2 r1 = cmad2(st.m10, v[lo], st.m11, t1);
+      v[hi].x = flip_sign(r1.x, sv);
+      v[hi].y = flip_sign(r1.y, sv);
+      v[lo] = r0;
     }
     if (ACC) {
-      nrm0 = fma(r0.x, r0.x, nrm0); nrm1 = fma(r0.y, r0.y, nrm1);
-      nrm0 = fma(r1.x, r1.x, nrm0); nrm1 = fma(r1.y, r1.y, nrm1);
+      nrm0 = fma(v[lo].x, v[lo].x, nrm0); nrm1 = fma(v[lo].y, v[lo].y, nrm1);
+      nrm0 = fma(v[hi].x, v[hi].x, nrm0); nrm1 = fma(v[hi].y, v[hi].y, nrm1);
     }
-    v[lo] = r0;
-    v[hi] = r1;
   }
 }
 
