@@ -15,8 +15,8 @@ import numpy as np  # noqa: E402
 from graphix_b200 import B200Statevector, mbqc  # noqa: E402
 from oracle.oracle import OracleStatevector, outcome_to_operator_matrix  # noqa: E402
 
-MODES = [{"fusion": 0}, {"fusion": 1}, {"fusion": 2}, {"fusion": 2, "strict": False}, {"fusion": 2, "strict": False, "batch": 3},
-         {"fusion": 2, "strict": False, "batch": 8}]
+MODES = [{"fusion": 0}, {"fusion": 1}, {"fusion": 2}, {"fusion": 2, "batch": 0}, {"fusion": 2, "strict": False, "batch": 0},
+         {"fusion": 2, "strict": False, "batch": 3}, {"fusion": 2, "strict": False, "batch": 12}]
 STATES = [mbqc.BasicStates.PLUS, mbqc.BasicStates.MINUS, mbqc.BasicStates.ZERO, mbqc.BasicStates.ONE,
           mbqc.BasicStates.PLUS_I, mbqc.PlanarState(mbqc.Plane.YZ, 0.37), mbqc.PlanarState(mbqc.Plane.XZ, 1.21),
           mbqc.PlanarState(mbqc.Plane.XY, 0.77)]
