@@ -614,6 +614,19 @@ def gpu_arm(args) -> None:
             del b2
             free_device_memory()
 
+    # N > 1: the sharded library default (strict: reference error timing; analytic projections are queued, every other
+    # projection waits for its all-reduced norm)
+    if world > 1 and args.fusion == 2 and args.nonstrict and not args.no_per_command and args.selector != "random":
+        b2 = make_gpu_backend(world, width, selector, nonstrict=False, batch=args.batch, device=local_rank, pattern=pattern,
+                              schedule=not args.no_schedule)
+        nst = max(2, args.steps - 2)
+        ms2, st2 = timed_pattern(timer, b2, pattern, nst, 2, run_kwargs, sharded=True)
+        strict_lazy = {"fusion": 2, "strict": True, "batch": args.batch, "value": ncmd * nst / (ms2 * 1e-3), "unit": UNIT,
+                       "ms_per_step": ms2 / nst, "steps": nst, "warmup": 2, "kernels": kernel_table(st2, nst, peak),
+                       "note": "ShardedStatevectorBackend default (strict=True): zero-norm RuntimeError raised by measure() itself"}
+        del b2
+        free_device_memory()
+
     # ---- end-to-end arm: host input vector in, host final state out ------------
     e2e = None
     if world == 1 and not args.no_e2e and len(pattern.input_nodes) <= 28:

@@ -95,6 +95,7 @@ struct gxsv {
   int profile = 0;
   int batch_axes = MAX_BATCH_AXES;   // distinct physical bits per batched pass (GXSV_BATCH_AXES)
   int chunk_log2 = DEFAULT_CHUNK_LOG2;
+  int dist_queue = 0;      // sharded strict mode: the orchestrator accepts queued (analytic) projections, see GXSV_OPT_DIST_QUEUE
   int tile_regs = 4;       // register axes per phase of k_fused_tile (GXSV_TILE_REGS = 3 | 4; measured on config 2: 4 ->
                            // 0.378 ms per pass / 44.8 k commands/s, 3 -> 0.518 ms / 32.9 k)
   int analytic_norms = 1;  // skip the norm accumulation of stages whose outcome probability is known to be 1/2
@@ -116,6 +117,7 @@ struct gxsv {
   // end of a pattern then cost no pass: read-outs apply the frame on the fly, anything else makes it real first.
   uint64_t fx = 0, fz = 0;
   bool lazy_frame = true;
+  bool attr_tile = false, attr_tma = false;   // dynamic shared-memory opt-in done for this handle's device
   double2* peer_psi[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double2* exported_psi = nullptr;
 };
@@ -459,10 +461,9 @@ int flush_batch(gxsv_t* h) {
   } else if (h->use_tma && plan_tma(h, bt, &g_tma, &g_tma_holes)) {
     const uint64_t ntiles = 1ull << (n - TILE_LOG2);
     const size_t dyn = (sizeof(double2) << TILE_LOG2) * TMA_BUFS;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->attr_tma) {      // per handle: function attributes belong to the device context
       CU(cudaFuncSetAttribute(k_fused_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-      attr_set = true;
+      h->attr_tma = true;
     }
     const uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * 2);   // persistent: 2 resident CTAs per SM
     Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n), /*frame_aware=*/true);   // a pending frame was issued AFTER these stages
@@ -491,11 +492,10 @@ int flush_batch(gxsv_t* h) {
     if (tb.nphases > MAX_PHASES) return fail(h, GXSV_EVALUE, "internal: batch needs %d phases", tb.nphases);
     const uint64_t ntiles = 1ull << (n - (8 + R));            // CTA iterations: 8 warp tiles of 2^(5+R) amplitudes
     const size_t dyn = sizeof(double2) << (8 + R);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->attr_tile) {     // per handle: function attributes belong to the device context
       CU(cudaFuncSetAttribute(k_fused_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 11)));
       CU(cudaFuncSetAttribute(k_fused_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 12)));
-      attr_set = true;
+      h->attr_tile = true;
     }
     uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * (R == 3 ? 4 : 2));   // persistent: resident CTAs only
     int gl = h->chunk_log2;
@@ -1028,6 +1028,9 @@ int gxsv_set_option(gxsv_t* h, int key, int value) {
     case GXSV_OPT_TMA:
       h->use_tma = value ? 1 : 0;
       return GXSV_OK;
+    case GXSV_OPT_DIST_QUEUE:
+      h->dist_queue = value ? 1 : 0;
+      return GXSV_OK;
     case GXSV_OPT_TILE_REGS:
       if (value != 3 && value != 4) return fail(h, GXSV_EVALUE, "tile register axes must be 3 or 4");
       { int rc = flush_batch(h); if (rc) return rc; }
@@ -1048,6 +1051,7 @@ int gxsv_get_option(gxsv_t* h, int key, int* value) {
     case GXSV_OPT_CHUNK_LOG2: *value = h->chunk_log2; return GXSV_OK;
     case GXSV_OPT_TMA: *value = h->use_tma; return GXSV_OK;
     case GXSV_OPT_TILE_REGS: *value = h->tile_regs; return GXSV_OK;
+    case GXSV_OPT_DIST_QUEUE: *value = h->dist_queue; return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -1479,7 +1483,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
         // mode always, and in STRICT mode whenever the outcome probability is analytic: such a projection cannot be the
         // zero-norm branch the reference raises for (statevec.py:1192-1193), and the half the reference keeps is known,
         // so nothing about it has to be waited for — error timing and results stay exactly the reference's.
-        if (h->batch_max > 0 && (!h->strict || (analytic && !h->dist))) {
+        if (h->batch_max > 0 && (!h->strict || (analytic && (!h->dist || h->dist_queue)))) {
           int ax = -1;
           for (int a = 0; a < h->batch.naxes; ++a) if (h->batch.axbit[a] == p) ax = a;
           // more than three axes need a CTA tile of 2^11 amplitudes (k_fused_tile)
@@ -1900,8 +1904,8 @@ int gxsv_set_norm(gxsv_t* h, double total_norm2) {
   if (!(total_norm2 > 0.0)) return fail(h, GXSV_EZERONORM, "set_norm: non-positive norm");
   // total_norm2 is the norm^2 of hscale * stored over all ranks; the modulus of the host scalar moves into g so that
   // neither drifts (batched stages leave their scalar factors in hscale, see gxsv_project_qubit)
-  // (non-blocking sharded mode only: there total_norm2 is by construction the norm^2 of hscale * stored)
-  const bool fold = h->dist && !h->strict && std::abs(h->hscale) > 0.0;
+  // (sharded modes with queued projections only: there total_norm2 is by construction the norm^2 of hscale * stored)
+  const bool fold = h->dist && (!h->strict || h->dist_queue) && std::abs(h->hscale) > 0.0;
   const double habs = fold ? std::abs(h->hscale) : 1.0;
   const double g = habs / std::sqrt(total_norm2);
   if (fold) h->hscale /= habs;

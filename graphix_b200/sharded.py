@@ -50,6 +50,11 @@ class GpuShardEngine:
         self.sv = B200Statevector(nqubit=0, max_qubits=local_bits, device=device, fusion=2, strict=strict,
                                   batch=0 if strict else batch)   # strict sharded projections wait for the all-reduced norm
         self.sv.set_option(_lib.OPT_DIST, 1)
+        if strict and batch:
+            # strict sharded mode: projections whose outcome probability is analytic (they cannot fail) are queued and
+            # share passes; project_local then returns NaN norms and the orchestrator collects the norms later
+            self.sv.set_option(_lib.OPT_BATCH, batch)
+            self.sv.set_option(_lib.OPT_DIST_QUEUE, 1)
         # what was really allocated: the constructor may have fallen back to half the requested register (lazy fusion
         # rarely needs the last qubit); qubits beyond it go to free rank bits instead of failing later
         self.capacity = self.sv.max_qubits
@@ -493,39 +498,40 @@ class ShardedStatevector:
         w = abs(self.u[self.rank]) ** 2
         scale = 1.0 / (1 << self._dead())
         li = qb.li
+        # phase convention: the reference keeps half 0 of the projected pair unless its norm is <= 1e-10
+        # (statevec.py:1187-1190).  For a queued projection: guess now, correct in _renorm() once the norm is known.
+        phi, assumed = 1.0 + 0j, False
+        if big == 1:
+            c = 0 if abs(m[1, 0]) >= abs(m[1, 1]) else 1
+            ratio = m[0, c] / m[1, c]
+            phi = complex(ratio / abs(ratio)) if abs(ratio) > 0 else 1.0 + 0j
+            assumed = bool(r0 > 1e-10 * r1)
         if not self.strict:
             # non-blocking: the engine queues / launches the projection (consecutive ones share a pass) and nothing
             # waits; the norms of a whole window are all-reduced, checked and used to renormalise in _renorm()
             self.engine.project_local_async(li, m)
-            # phase convention: the reference keeps half 0 of the projected pair unless its norm is <= 1e-10
-            # (statevec.py:1187-1190).  Guess now, correct in _renorm() once the norm is known.
-            phi, assumed = 1.0 + 0j, False
-            if big == 1:
-                c = 0 if abs(m[1, 0]) >= abs(m[1, 1]) else 1
-                ratio = m[0, c] / m[1, c]
-                phi = complex(ratio / abs(ratio)) if abs(ratio) > 0 else 1.0 + 0j
-                assumed = bool(r0 > 1e-10 * r1)
-                if assumed:
-                    self.engine.scale_host(phi)
-            self._window.append((w * scale, big, (r0 / r1) if big else (r1 / r0 if r0 > 0 else 0.0), phi, assumed, qubit))
-            self._remove(qb)
-            for o in self.q:
-                if o.li is not None and o.li > li:
-                    o.li -= 1
-            if len(self._window) >= self.WINDOW:
-                self._renorm()
-            return
-        n0l, n1l = self.engine.project_local(li, m)
-        n0, n1 = self._allreduce([w * n0l, w * n1l])
-        n0, n1 = n0 * scale, n1 * scale
+            n0l = n1l = math.nan
+        else:
+            # strict: the engine returns the local half-norms — or NaN when it queued the projection because its outcome
+            # probability is analytic (it cannot be the zero-norm branch, nothing has to be waited for)
+            n0l, n1l = self.engine.project_local(li, m)
         self._remove(qb)
         for o in self.q:
             if o.li is not None and o.li > li:
                 o.li -= 1
+        if math.isnan(n0l):
+            if big == 1 and assumed:
+                self.engine.scale_host(phi)
+            self._window.append((w * scale, big, (r0 / r1) if big else (r1 / r0 if r0 > 0 else 0.0), phi, assumed, qubit))
+            if len(self._window) >= self.WINDOW:
+                self._renorm()
+            return
+        # synchronous projection; queued projections still pending are resolved in the same all-reduce
+        prev, (n0, n1) = self._renorm(extra=[w * n0l * scale, w * n1l * scale], set_norm=False)
         pick = 0
-        if n0 <= 1e-10:
+        if n0 <= 1e-10 * prev:
             pick = 1
-            if n1 <= 1e-10:
+            if n1 <= 1e-10 * prev:
                 raise RuntimeError(f"Attempted to remove qubit {qubit} from 0-norm statevector.")
         self.engine.set_norm(n1 if big else n0)
         if pick != big:
@@ -850,11 +856,15 @@ class ShardedStatevector:
         self.engine.reset()
         self._clear()
 
-    def _renorm(self) -> None:
-        """Non-strict mode: collect the local norms of the projections issued since the last call, all-reduce them,
-        raise the zero-norm RuntimeError of any of them, and set the normalisation of the current state."""
+    def _renorm(self, extra: Sequence[float] | None = None, set_norm: bool = True):
+        """Collect the local norms of the projections queued since the last call, all-reduce them (together with the
+        already weighted local values ``extra`` of a synchronous projection, if any), raise the zero-norm RuntimeError of
+        any of them, and — unless a synchronous projection is about to do it — set the normalisation of the current
+        state.  Returns (norm^2 of the state after the window relative to a normalised start, reduced ``extra``)."""
         if not self._window:
-            return
+            if extra is None:
+                return 1.0, []
+            return 1.0, self._allreduce(list(extra))
         import time  # noqa: PLC0415
 
         t0 = time.perf_counter()
@@ -865,7 +875,10 @@ class ShardedStatevector:
             raise RuntimeError(f"sharded state: {len(local)} norms for {len(window)} projections")
         # a negative entry is MINUS the analytic ratio (norm after / norm before) of a projection whose norm the engine did
         # not accumulate (outcome probability known to be 1/2, see gxsv_take_norms); the same on every rank
-        tot = self._allreduce([rec[0] * n if n >= 0 else 0.0 for rec, n in zip(window, local, strict=True)])
+        vals = [rec[0] * n if n >= 0 else 0.0 for rec, n in zip(window, local, strict=True)]
+        nw = len(vals)
+        red = self._allreduce(vals + list(extra or []))
+        tot, red_extra = red[:nw], red[nw:]
         prev = 1.0                       # the window starts from a normalised state (g was set by the last _renorm)
         for i, ((_, big, ratio, phi, assumed, qubit), n) in enumerate(zip(window, tot, strict=True)):
             if local[i] < 0:
@@ -877,7 +890,9 @@ class ShardedStatevector:
             if big and (n0 > 1e-10) != assumed:
                 self.engine.scale_host(phi if n0 > 1e-10 else phi.conjugate())
             prev = n
-        self.engine.set_norm(tot[-1])
+        if set_norm:
+            self.engine.set_norm(tot[-1])
+        return prev, red_extra
 
     def check_deferred(self) -> None:
         self._renorm()

@@ -60,8 +60,11 @@ enum {
   GXSV_OPT_CHUNK_LOG2 = 7, /* tuning: log2 of the consecutive blocks / tiles a CTA of a batched pass takes at a time */
   GXSV_OPT_TMA = 8,        /* 1 = batched passes stage CTA tiles through shared memory with bulk copies (cp.async.bulk +
                             * mbarrier) whenever the layout allows; 0 (default) = register-staged kernels */
-  GXSV_OPT_TILE_REGS = 9   /* tuning: register axes per phase of the multi-axis batched pass: 3 (2^3 amplitudes per thread,
+  GXSV_OPT_TILE_REGS = 9,  /* tuning: register axes per phase of the multi-axis batched pass: 3 (2^3 amplitudes per thread,
                             * 4 CTAs per SM) or 4 (default: 2^4 per thread, 2 CTAs per SM, fewer phases) */
+  GXSV_OPT_DIST_QUEUE = 10 /* sharded STRICT mode: 1 = projections whose outcome probability is analytic are queued like in
+                            * the single-GPU strict mode (gxsv_project_qubit then returns NaN norms and the caller collects
+                            * them later with gxsv_take_norms); everything else still returns its local half-norms at once */
 };
 
 /* kernel kinds reported by gxsv_profile_read / gxsv_stats */
