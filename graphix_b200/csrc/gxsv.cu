@@ -95,6 +95,7 @@ struct gxsv {
   int profile = 0;
   int batch_axes = MAX_BATCH_AXES;   // distinct physical bits per batched pass (GXSV_BATCH_AXES)
   int chunk_log2 = DEFAULT_CHUNK_LOG2;
+  int max_phases = MAX_PHASES;   // register phases one batched pass may need (GXSV_MAX_PHASES = 1..4)
   int dist_queue = 0;      // sharded strict mode: the orchestrator accepts queued (analytic) projections, see GXSV_OPT_DIST_QUEUE
   int tile_regs = 4;       // register axes per phase of k_fused_tile (GXSV_TILE_REGS = 3 | 4; measured on config 2: 4 ->
                            // 0.378 ms per pass / 44.8 k commands/s, 3 -> 0.518 ms / 32.9 k)
@@ -904,6 +905,7 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
     if (v >= 1 && v <= MAX_TILE_AXES) h->batch_axes = v;
   }
   if (const char* tm = std::getenv("GXSV_TMA")) h->use_tma = std::atoi(tm) ? 1 : 0;
+  if (const char* mp = std::getenv("GXSV_MAX_PHASES")) { const int v = std::atoi(mp); if (v >= 1 && v <= MAX_PHASES) h->max_phases = v; }
   if (const char* lf = std::getenv("GXSV_LAZY_FRAME")) h->lazy_frame = std::atoi(lf) != 0;
   if (const char* tr = std::getenv("GXSV_TILE_REGS")) h->tile_regs = (std::atoi(tr) == 3) ? 3 : 4;
   if (const char* an = std::getenv("GXSV_ANALYTIC_NORMS")) h->analytic_norms = std::atoi(an) ? 1 : 0;
@@ -1494,7 +1496,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
             Batch& b = h->batch;
             b.st[b.nstages].axis = (ax < 0) ? b.naxes : ax;
             b.nstages += 1;
-            full = plan_phases(b, nullptr, h->tile_regs) > MAX_PHASES;
+            full = plan_phases(b, nullptr, h->tile_regs) > h->max_phases;
             b.nstages -= 1;
           }
           if (full) {
