@@ -650,18 +650,30 @@ def gpu_arm(args) -> None:
                "ms_per_step": e2e_ms / args.steps}
 
     if world > 1 and not args.no_e2e and width - (world.bit_length() - 1) <= 30:
-        # end to end on N GPUs: the inputs are product states (nothing to upload), the result of every step is
-        # delivered to pinned HOST memory: every rank reads back its shard of the final state
+        # end to end on N GPUs: every rank uploads ITS slice of the joint input state from pinned host memory (the same
+        # |+..+> input as at N = 1, handed over shard by shard) and reads its shard of the final state back
+        from graphix_b200.sharded import ShardedInput
+
         eng = backend.state.engine
+        n_in = len(pattern.input_nodes)
+        kl_max = min(n_in, eng.capacity)
+        host_in = torch.full((1 << kl_max,), 2.0 ** (-n_in / 2), dtype=torch.complex128).pin_memory()
+        np_in = host_in.numpy()
+        h2d = {"bytes": 0}
+
+        def slice_for(t, kg, kl):
+            h2d["bytes"] = 16 << kl
+            return np_in[: 1 << kl]
+
         np_out = None
 
         def e2e_step_sharded() -> None:
             backend.state.reset()
             backend.node_index.clear()
-            PatternSimulator(pattern, backend).run()
+            PatternSimulator(pattern, backend).run(input_state=ShardedInput(n_in, slice_for))   # H2D inside
             backend.state.check_deferred()
             if np_out is not None:
-                eng.sv.flatten(out=np_out)
+                eng.sv.flatten(out=np_out)                                                       # D2H inside
 
         e2e_step_sharded()          # untimed: learn the size of the local shard of the output state
         host_out = torch.empty(1 << eng.nqubit, dtype=torch.complex128).pin_memory()
@@ -671,9 +683,10 @@ def gpu_arm(args) -> None:
         t = torch.tensor([max(e2e_dev, timer.wall_ms)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-        e2e = {"value": ncmd * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+        e2e = {"value": ncmd * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": world * h2d["bytes"],
                "d2h_bytes_per_step": world * (16 << eng.nqubit), "ms_per_step": e2e_ms / args.steps,
-               "note": "inputs are |+> product states (no upload); every rank reads its shard of the final state back"}
+               "note": "every rank uploads its slice of the joint |+..+> input vector from pinned host memory and reads "
+                       "its shard of the final state back to pinned host memory"}
 
     # ---- the GPU arm on exactly the command window the CPU baseline is timed on ------------------------------
     same_window = None

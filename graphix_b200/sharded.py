@@ -177,6 +177,18 @@ class GpuShardEngine:
         self.sv.set_option(key, value)
 
 
+class ShardedInput:
+    """A joint input state of ``nqubit`` qubits handed over shard by shard, for inputs too large (or too wasteful) to
+    build in full on every rank: ``slice_for(t, kg, kl)`` returns the ``2**kl`` amplitudes (C-contiguous complex128,
+    ideally pinned host memory) of the joint vector whose first ``kg`` qubits (first = MSB) have the value ``t``.  Accepted
+    by ``ShardedStatevector.add_nodes`` / ``ShardedStatevectorBackend.add_nodes`` in place of a ``2**nqubit`` vector
+    (graphix/sim/statevec.py:186-205); normalisation is the caller's responsibility."""
+
+    def __init__(self, nqubit: int, slice_for) -> None:
+        self.nqubit = int(nqubit)
+        self.slice_for = slice_for
+
+
 class _Q:
     """Location of one logical qubit: local engine index ``li`` or global bit ``g``."""
 
@@ -317,6 +329,11 @@ class ShardedStatevector:
 
     def add_nodes(self, nqubit: int, data) -> None:
         """statevec.py:269-300: product states qubit by qubit, joint 2^k vectors sliced over the ranks."""
+        if isinstance(data, ShardedInput):
+            if nqubit is not None and nqubit != data.nqubit:
+                raise ValueError(f"Mismatch between nqubit and inferred nqubit: {nqubit} != {data.nqubit}.")
+            self._add_vector(None, sharded=data)
+            return
         vec = self._joint_vector(nqubit, data)
         if vec is not None:
             self._add_vector(vec)
@@ -367,10 +384,10 @@ class ShardedStatevector:
             raise ValueError("Input state is not normalized.")
         return vec
 
-    def _add_vector(self, vec: np.ndarray) -> None:
+    def _add_vector(self, vec: np.ndarray | None, sharded: ShardedInput | None = None) -> None:
         """Tensor a joint vector of k new qubits onto the state.  The last qubits go to the shard while it has room,
         the first ones take free rank bits: every rank keeps the slice of ``vec`` that its rank bits select."""
-        k = int(vec.size).bit_length() - 1
+        k = sharded.nqubit if sharded is not None else int(vec.size).bit_length() - 1
         kl = min(k, self.engine.capacity - self.engine.nqubit)
         kg = k - kl
         free = [b for b in range(self.gbits) if self.owner[b] is None]
@@ -385,7 +402,12 @@ class ShardedStatevector:
             self.flip[b] = 0
             t = (t << 1) | ((self.rank >> b) & 1)
             new_q.append(qb)
-        mine = vec.reshape(1 << kg, 1 << kl)[t]
+        if sharded is not None:
+            mine = np.asarray(sharded.slice_for(t, kg, kl))
+            if mine.shape != (1 << kl,):
+                raise ValueError(f"ShardedInput.slice_for returned shape {mine.shape}, expected ({1 << kl},)")
+        else:
+            mine = vec.reshape(1 << kg, 1 << kl)[t]
         first = self.engine.nqubit
         if kl:
             self.engine.tensor(mine)
@@ -985,4 +1007,4 @@ class ShardedStatevectorBackend(B200StatevectorBackend):
         self.state.check_deferred()
 
 
-__all__ = ["GpuShardEngine", "ShardedStatevector", "ShardedStatevectorBackend", "BasicStates"]
+__all__ = ["GpuShardEngine", "ShardedInput", "ShardedStatevector", "ShardedStatevectorBackend", "BasicStates"]

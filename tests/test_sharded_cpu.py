@@ -208,7 +208,13 @@ def case_vector_inputs(rank, world, engine_factory=None):
         if seed % 3 == 0:
             vec[: 1 << (k - 1)] = 0.0          # first new qubit in |1>: exact zeros in some ranks' slices
         vec /= np.linalg.norm(vec)
-        sh.add_nodes(k, vec if seed % 2 else list(vec))
+        if seed % 4 == 1:
+            # the same joint vector handed over shard by shard (ShardedInput: no rank ever sees the full vector)
+            from graphix_b200.sharded import ShardedInput
+
+            sh.add_nodes(k, ShardedInput(k, lambda t, kg, kl, vec=vec: np.ascontiguousarray(vec.reshape(1 << kg, 1 << kl)[t])))
+        else:
+            sh.add_nodes(k, vec if seed % 2 else list(vec))
         orc.add_nodes(k, vec)
         assert sh.nqubit == orc.nqubit
         np.testing.assert_allclose(sh.flatten(), orc.flatten(), atol=1e-12, err_msg=f"seed {seed} after add")
