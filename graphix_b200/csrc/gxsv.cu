@@ -102,6 +102,9 @@ struct gxsv {
   int analytic_norms = 1;  // skip the norm accumulation of stages whose outcome probability is known to be 1/2
   int use_tma = 0;         // 1: batched passes stage CTA tiles through shared memory with bulk copies (k_fused_tma; measured slower for many
                            // stages per pass, see kernels.cuh) when the layout allows
+  int tile_prefetch = 0;          // 1: k_fused_tile asks its next warp tile into L2 (GXSV_TILE_PREFETCH=1; measured slower: 42.1 k
+                                  // against 49.5 k commands/s on config 2, 4.0 k against 5.3 k on config 3 — kept as an option)
+  bool defer_partner_cz = true;   // batched stages leave the partner's CZs queued (GXSV_DEFER_VCZ=0: apply them in the stage)
   int batch_max = 0;       // > 0: queue up to this many fused projections and run them in one pass (non-strict only)
   Batch batch;             // the open batch (nstages == 0: none)
   std::vector<Deferred> deferred;   // projections awaiting their norm check (non-strict mode)
@@ -490,6 +493,7 @@ int flush_batch(gxsv_t* h) {
     for (int k = 0; k < bt.nstages; ++k) { tb.st[k] = bt.st[k]; tb.nscale[k] = bt.nscale[k]; }
     const int R = h->tile_regs;
     tb.nphases = plan_phases(bt, &tb, R);
+    tb.prefetch = h->tile_prefetch;
     if (tb.nphases > MAX_PHASES) return fail(h, GXSV_EVALUE, "internal: batch needs %d phases", tb.nphases);
     const uint64_t ntiles = 1ull << (n - (8 + R));            // CTA iterations: 8 warp tiles of 2^(5+R) amplitudes
     const size_t dyn = sizeof(double2) << (8 + R);
@@ -501,6 +505,13 @@ int flush_batch(gxsv_t* h) {
     uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * (R == 3 ? 4 : 2));   // persistent: resident CTAs only
     int gl = h->chunk_log2;
     while (gl > 0 && (ntiles >> gl) < tgrid * 8) --gl;
+    static const bool log_shapes = std::getenv("GXSV_BATCH_LOG") != nullptr;
+    if (log_shapes) {
+      int nuni = 0;
+      for (int k = 0; k < bt.nstages; ++k) nuni += (tb.st[k].qtab == 0ull && tb.st[k].kind == 0 && !tb.st[k].acc) ? 1 : 0;
+      fprintf(stderr, "gxsv-pass n=%d axes=%d stages=%d phases=%d uniform=%d bits=", n, bt.naxes, bt.nstages, tb.nphases, nuni);
+      for (int a = 0; a < bt.naxes; ++a) fprintf(stderr, "%d%s", (int)bt.axbit[a], a + 1 < bt.naxes ? "," : "\n");
+    }
     Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n), /*frame_aware=*/true);   // a pending frame was issued AFTER these stages
     if (R == 3) k_fused_tile<3><<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm);
     else k_fused_tile<4><<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm);
@@ -907,6 +918,8 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
   if (const char* tm = std::getenv("GXSV_TMA")) h->use_tma = std::atoi(tm) ? 1 : 0;
   if (const char* mp = std::getenv("GXSV_MAX_PHASES")) { const int v = std::atoi(mp); if (v >= 1 && v <= MAX_PHASES) h->max_phases = v; }
   if (const char* lf = std::getenv("GXSV_LAZY_FRAME")) h->lazy_frame = std::atoi(lf) != 0;
+  if (const char* tp = std::getenv("GXSV_TILE_PREFETCH")) h->tile_prefetch = std::atoi(tp) != 0;
+  if (const char* dv = std::getenv("GXSV_DEFER_VCZ")) h->defer_partner_cz = std::atoi(dv) != 0;
   if (const char* tr = std::getenv("GXSV_TILE_REGS")) h->tile_regs = (std::atoi(tr) == 3) ? 3 : 4;
   if (const char* an = std::getenv("GXSV_ANALYTIC_NORMS")) h->analytic_norms = std::atoi(an) ? 1 : 0;
   if (const char* cl = std::getenv("GXSV_CHUNK_LOG2")) {
@@ -1033,6 +1046,12 @@ int gxsv_set_option(gxsv_t* h, int key, int value) {
     case GXSV_OPT_DIST_QUEUE:
       h->dist_queue = value ? 1 : 0;
       return GXSV_OK;
+    case GXSV_OPT_TILE_PREFETCH:
+      h->tile_prefetch = value ? 1 : 0;
+      return GXSV_OK;
+    case GXSV_OPT_DEFER_VCZ:
+      h->defer_partner_cz = value != 0;
+      return GXSV_OK;
     case GXSV_OPT_TILE_REGS:
       if (value != 3 && value != 4) return fail(h, GXSV_EVALUE, "tile register axes must be 3 or 4");
       { int rc = flush_batch(h); if (rc) return rc; }
@@ -1054,6 +1073,8 @@ int gxsv_get_option(gxsv_t* h, int key, int* value) {
     case GXSV_OPT_TMA: *value = h->use_tma; return GXSV_OK;
     case GXSV_OPT_TILE_REGS: *value = h->tile_regs; return GXSV_OK;
     case GXSV_OPT_DIST_QUEUE: *value = h->dist_queue; return GXSV_OK;
+    case GXSV_OPT_TILE_PREFETCH: *value = h->tile_prefetch; return GXSV_OK;
+    case GXSV_OPT_DEFER_VCZ: *value = h->defer_partner_cz ? 1 : 0; return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }
 }
@@ -1449,7 +1470,7 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
       }
       const int vid = (vi >= 0) ? h->q[vi].id : -1;
       uint64_t mq = 0, mv = 0;
-      std::vector<std::pair<int, int>> keep;
+      std::vector<std::pair<int, int>> keep, vedges;   // vedges: CZs of v with materialised qubits (what mv encodes)
       for (auto& e : h->pend) {
         const bool tq = (e.first == qid || e.second == qid);
         const bool tv = (vid >= 0) && (e.first == vid || e.second == vid);
@@ -1458,7 +1479,8 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
           mq |= 1ull << by_id(h, e.first == qid ? e.second : e.first)->phys;
         } else if (tv) {
           Qubit* o = by_id(h, e.first == vid ? e.second : e.first);
-          if (o->phys >= 0) mv |= 1ull << o->phys; else keep.push_back(e);  // virtual-virtual edges stay queued
+          if (o->phys >= 0) { mv |= 1ull << o->phys; vedges.push_back(e); }
+          else keep.push_back(e);  // virtual-virtual edges stay queued
         } else {
           keep.push_back(e);
         }
@@ -1505,6 +1527,14 @@ int gxsv_project_qubit(gxsv_t* h, int q, const double m[8], double atol, double 
             ax = -1;
           }
           if (ax < 0) { ax = h->batch.naxes++; h->batch.axbit[ax] = (unsigned char)p; }
+          // A queued stage applies no partner signs: the CZs of v with materialised qubits stay queued (both ends are
+          // materialised once the stage has run) until one of their ends is measured — there they are part of that
+          // stage's mq, which costs the same two sign XORs per pair whatever its weight — or until another kernel needs
+          // the register (flush_pending, one diagonal pass).  The common stage then flips one half of its inputs only.
+          if (h->defer_partner_cz) {
+            h->pend.insert(h->pend.end(), vedges.begin(), vedges.end());
+            mv = 0;
+          }
           Stage& st = h->batch.st[h->batch.nstages++];
           st.m00 = d2(s0 * c0); st.m01 = d2(s0 * c1); st.m10 = d2(s1 * c0); st.m11 = d2(-s1 * c1);
           st.mq = mq; st.mv = mv; st.axis = ax; st.qtab = st.vtab = 0; st.pad = 0;

@@ -69,6 +69,7 @@ __device__ __forceinline__ double cnorm2(const double2 a) { return fma(a.x, a.x,
 
 // streaming accesses: the state is touched once per pass and is far larger than L2
 __device__ __forceinline__ double2 ld_amp(const double2* p) { return __ldcs(p); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p))); }
 __device__ __forceinline__ void st_amp(double2* p, const double2 v) { __stcs(p, v); }
 
 // ---------------------------------------------------------------------------
@@ -424,40 +425,57 @@ __device__ __forceinline__ double flip_sign(const double x, const unsigned int s
 }
 
 // The 2^(NB-1) amplitude pairs of one stage on register axis AX.  KIND as in Stage; ACC = accumulate the norm^2 of
-// the results (two chains).  For kinds 0 / 1 with |a| = 1 — every XY-plane measurement of a qubit whose partner was
-// prepared in |+> — the norm after the stage is exactly 2 |in|^2 whatever the data (the outcome probability of such a
-// measurement is 1/2), so the host asks for the accumulation only where it cannot know the answer (Stage::acc).
-template <int NB, int AX, int KIND, bool ACC>
+// the results (two chains); HASV = the new qubit's half takes a sign (CZs of the partner with materialised qubits, or a
+// |-> partner).  For kinds 0 / 1 with |a| = 1 — every XY-plane measurement of a qubit whose partner was prepared in
+// |+> — the norm after the stage is exactly 2 |in|^2 whatever the data (the outcome probability of such a measurement
+// is 1/2), so the host asks for the accumulation only where it cannot know the answer (Stage::acc).
+// FP64 work of a kind 0 / 1 pair: SIX fused multiply-adds — r1 = t0 - a t1 as two chains of two, then the other output
+// from the first, r0 = 2 t0 - r1 (kind 1: r0 = a t0 + t1, r1 = r0 - 2 t1) — against 2 DMUL + 2 DFMA + 4 DADD for the
+// textbook form; the CZ sign of the measured qubit is XORed into t1 in place (two LOP3, no register moves), and the
+// batched path queues no partner signs at all (gxsv_project_qubit leaves those CZs queued until one of their ends is
+// measured, where they are the free sq of that stage), so the common stage is 6 DFMA + 2 LOP3 + 1 PRMT per pair.
+// UNIQ (kind 0 only): no CZ partner of the measured qubit sits on another register axis, so the sign of t1 is the same
+// for all pairs of the thread and is folded into the multiplier once (no per-pair sign work at all: 6 DFMA per pair).
+template <int NB, int AX, int KIND, bool ACC, bool HASV, bool UNIQ = false>
 __device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& st, const unsigned long long tq64,
                                             const unsigned long long tv64, double& nrm0, double& nrm1) {
-  const double2 a = st.a;
+  double2 a = st.a;
+  if (UNIQ) {
+    const unsigned int s = __byte_perm((unsigned int)tq64, 0u, 0x0444);
+    a.x = flip_sign(a.x, s);
+    a.y = flip_sign(a.y, s);
+  }
 #pragma unroll
   for (int lo = 0; lo < (1 << NB); ++lo) {
     if ((lo >> AX) & 1) continue;
     const int hi = lo | (1 << AX);
     const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded at compile time)
     const unsigned int tq = (k < 4) ? (unsigned int)tq64 : (unsigned int)(tq64 >> 32);
-    const unsigned int tv = (k < 4) ? (unsigned int)tv64 : (unsigned int)(tv64 >> 32);
-    const unsigned int sq = __byte_perm(tq, 0u, 0x0444 | ((k & 3) << 12)), sv = __byte_perm(tv, 0u, 0x0444 | ((k & 3) << 12));
-    // results are written straight into the slots they replace (fewer live temporaries: the unrolled stage variants
-    // then agree on where v[] lives and need no register moves where they join)
+    const unsigned int sq = UNIQ ? 0u : __byte_perm(tq, 0u, 0x0444 | ((k & 3) << 12));
+    unsigned int sv = 0u;
+    if (HASV) {
+      const unsigned int tv = (k < 4) ? (unsigned int)tv64 : (unsigned int)(tv64 >> 32);
+      sv = __byte_perm(tv, 0u, 0x0444 | ((k & 3) << 12));
+    }
+    const double t1x = UNIQ ? v[hi].x : flip_sign(v[hi].x, sq), t1y = UNIQ ? v[hi].y : flip_sign(v[hi].y, sq);
+    // order chosen so that every result can take the registers of the operand it replaces (two temporaries per pair):
+    // the half that needs both components of one input first, into that input's slot, then the other half in place
     if (KIND == 0) {
-      double2 w = cmul(a, v[hi]);
-      w.x = flip_sign(w.x, sq);
-      w.y = flip_sign(w.y, sq);
-      v[hi].x = flip_sign(v[lo].x - w.x, sv);
-      v[hi].y = flip_sign(v[lo].y - w.y, sv);
-      v[lo].x += w.x;
-      v[lo].y += w.y;
+      const double ux = fma(a.y, t1y, v[lo].x), uy = fma(-a.y, t1x, v[lo].y);
+      v[hi].x = fma(-a.x, t1x, ux);                 // r1 = t0 - a t1
+      v[hi].y = fma(-a.x, t1y, uy);
+      v[lo].x = fma(2.0, v[lo].x, -v[hi].x);        // r0 = t0 + a t1 = 2 t0 - r1
+      v[lo].y = fma(2.0, v[lo].y, -v[hi].y);
+      if (HASV) { v[hi].x = flip_sign(v[hi].x, sv); v[hi].y = flip_sign(v[hi].y, sv); }
     } else if (KIND == 1) {
-      const double2 u = cmul(a, v[lo]);
-      const double tx = flip_sign(v[hi].x, sq), ty = flip_sign(v[hi].y, sq);
-      v[hi].x = flip_sign(u.x - tx, sv);
-      v[hi].y = flip_sign(u.y - ty, sv);
-      v[lo].x = u.x + tx;
-      v[lo].y = u.y + ty;
+      const double ux = fma(-a.y, v[lo].y, t1x), uy = fma(a.y, v[lo].x, t1y);
+      v[lo].x = fma(a.x, v[lo].x, ux);              // r0 = a t0 + t1
+      v[lo].y = fma(a.x, v[lo].y, uy);
+      v[hi].x = fma(-2.0, t1x, v[lo].x);            // r1 = a t0 - t1 = r0 - 2 t1
+      v[hi].y = fma(-2.0, t1y, v[lo].y);
+      if (HASV) { v[hi].x = flip_sign(v[hi].x, sv); v[hi].y = flip_sign(v[hi].y, sv); }
     } else {
-      const double2 t1 = make_double2(flip_sign(v[hi].x, sq), flip_sign(v[hi].y, sq));
+      const double2 t1 = make_double2(t1x, t1y);
       const double2 r0 = cmad2(st.m00, v[lo], st.m01, t1);
       double2 r1 = cmad2(st.m10, v[lo], st.m11, t1);
       v[hi].x = flip_sign(r1.x, sv);
@@ -471,23 +489,26 @@ __device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& 
   }
 }
 
-// Apply stage `st` on register axis AX of the 2^NB amplitudes a thread holds; gpar_q / gpar_v = parity of the thread's
-// fixed physical index bits in st.mq / st.mv.  Adds the norm^2 of the 2^NB results to nrm0 / nrm1 when st.acc is set.
+// Apply stage `st` on register axis AX of the 2^NB amplitudes a thread holds; gfixed = the thread's fixed physical index
+// bits (their parity in st.mq / st.mv decides the thread-wide part of the signs).  Adds the norm^2 of the 2^NB results to nrm0 / nrm1 (the caller keeps
+// the sum only when st.acc is set; the rare variants always compute it — fewer code paths).
 template <int NB, int AX>
-__device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage& st, const unsigned int gpar_q,
-                                              const unsigned int gpar_v, double& nrm0, double& nrm1) {
+__device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage& st, const uint64_t gfixed,
+                                              double& nrm0, double& nrm1) {
   // byte k of tq / tv = 0x80 iff the k-th amplitude pair takes the sign
+  const unsigned int gpar_q = __popcll(gfixed & st.mq);
   const unsigned long long tq = st.qtab ^ ((gpar_q & 1u) ? 0x8080808080808080ull : 0ull);
-  const unsigned long long tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x8080808080808080ull : 0ull);
-  if (st.kind == 0) {
-    if (st.acc) stage_pairs<NB, AX, 0, true>(v, st, tq, tv, nrm0, nrm1);
-    else stage_pairs<NB, AX, 0, false>(v, st, tq, tv, nrm0, nrm1);
-  } else if (st.kind == 1) {
-    if (st.acc) stage_pairs<NB, AX, 1, true>(v, st, tq, tv, nrm0, nrm1);
-    else stage_pairs<NB, AX, 1, false>(v, st, tq, tv, nrm0, nrm1);
-  } else {
-    stage_pairs<NB, AX, 2, true>(v, st, tq, tv, nrm0, nrm1);
+  if (st.kind == 0 && st.mv == 0ull && !st.neg) {          // every stage of a transpiled pattern
+    if (st.acc) stage_pairs<NB, AX, 0, true, false>(v, st, tq, 0ull, nrm0, nrm1);
+    else if (st.qtab == 0ull) stage_pairs<NB, AX, 0, false, false, true>(v, st, tq, 0ull, nrm0, nrm1);
+    else stage_pairs<NB, AX, 0, false, false>(v, st, tq, 0ull, nrm0, nrm1);
+    return;
   }
+  const unsigned int gpar_v = __popcll(gfixed & st.mv);
+  const unsigned long long tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x8080808080808080ull : 0ull);
+  if (st.kind == 0) stage_pairs<NB, AX, 0, true, true>(v, st, tq, tv, nrm0, nrm1);
+  else if (st.kind == 1) stage_pairs<NB, AX, 1, true, true>(v, st, tq, tv, nrm0, nrm1);
+  else stage_pairs<NB, AX, 2, true, true>(v, st, tq, tv, nrm0, nrm1);
 }
 
 // Batch on at most three physical bits: a thread owns the 2^A amplitudes of one group in registers and applies the
@@ -528,12 +549,11 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_batch(double2* __restrict__ ps
     }
     for (int s = 0; s < bt.nstages; ++s) {
       const Stage& st = bt.st[s];
-      const unsigned int pq = __popcll(base & st.mq), pv = __popcll(base & st.mv);
       double n0 = 0.0, n1 = 0.0;
       const int la = st.axis;
-      if (la == 0) stage_on_axis<A, 0>(v, st, pq, pv, n0, n1);
-      if (A > 1 && la == 1) stage_on_axis<A, (A > 1 ? 1 : 0)>(v, st, pq, pv, n0, n1);
-      if (A > 2 && la == 2) stage_on_axis<A, (A > 2 ? 2 : 0)>(v, st, pq, pv, n0, n1);
+      if (la == 0) stage_on_axis<A, 0>(v, st, base, n0, n1);
+      if (A > 1 && la == 1) stage_on_axis<A, (A > 1 ? 1 : 0)>(v, st, base, n0, n1);
+      if (A > 2 && la == 2) stage_on_axis<A, (A > 2 ? 2 : 0)>(v, st, base, n0, n1);
       if (st.acc) sacc[s][threadIdx.x] += n0 + n1;
     }
 #pragma unroll
@@ -566,7 +586,8 @@ constexpr int WTILE_LOG2 = 8;      // amplitudes per warp tile
 constexpr int MAX_TILE_AXES = 7;
 constexpr int MAX_PHASES = 4;
 struct TileBatch {
-  int nstages, naxes, nphases, pad;
+  int nstages, naxes, nphases;
+  int prefetch;                               // != 0: ask the next warp tile into L2 while the current one is computed
   unsigned char lax[MAX_STAGES];              // register slot (0..R-1) of the axis of every stage inside its phase
   unsigned char s_begin[MAX_PHASES], s_end[MAX_PHASES];
   // everything a thread needs to address its 2^R amplitudes is tabulated by the host (no per-tile index arithmetic):
@@ -600,68 +621,86 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
   const int r = lane >> F;
   const double g = ctrl->g;
   const int nphases = bt.nphases;
+  const bool pf = bt.prefetch != 0;
+  const unsigned int pfmask = (F >= 3) ? 7u : ((1u << F) - 1u);   // lanes that start a 128-byte line (or a shorter run)
 #pragma unroll
   for (int k = 0; k < MAX_STAGES; ++k) sacc[k][tid] = 0.0;
-  const uint64_t nchunks = (ntiles + (1ull << glog) - 1ull) >> glog;
-  for (uint64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    for (uint64_t it = 0; it < (1ull << glog); ++it) {
-      const uint64_t t = (chunk << glog) + it;
-      if (t >= ntiles) break;
-      const uint64_t wt = t * (TPB / 32) + warp;    // this warp's tile
-      const uint64_t base = expand((wt << F) | f, hs);
-      double2 v[D];
-      // offsets of the axis values fixed per lane: uniform table entries selected by the bits of r (a table indexed by
-      // r itself — a per-thread index into the kernel parameters — faulted on sm_100a with CUDA 12.9 although the
-      // emulated addresses were all in range; the uniform form costs three predicated ORs)
-      auto lane_off = [&](int p, uint64_t& go, unsigned int& so) {
-        go = base;
-        so = fsw;
+  // the i-th CTA tile of this CTA: chunks of 2^glog consecutive tiles, chunks dealt round robin (monotonic in i)
+  const uint64_t gmask = (1ull << glog) - 1ull;
+  auto tile_of = [&](uint64_t i) { return (((uint64_t)blockIdx.x + (i >> glog) * gridDim.x) << glog) + (i & gmask); };
+  auto base_of = [&](uint64_t t) { return expand(((t * (TPB / 32) + warp) << F) | f, hs); };
+  uint64_t i = 0, t = tile_of(0);
+  uint64_t base_next = (t < ntiles) ? base_of(t) : 0ull;
+  while (t < ntiles) {
+    const uint64_t base = base_next;
+    double2 v[D];
+    // offsets of the axis values fixed per lane: uniform table entries selected by the bits of r (a table indexed by
+    // r itself — a per-thread index into the kernel parameters — faulted on sm_100a with CUDA 12.9 although the
+    // emulated addresses were all in range; the uniform form costs three predicated ORs)
+    auto lane_off = [&](int p, uint64_t bs, uint64_t& go, unsigned int& so) {
+      go = bs;
+      so = fsw;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-          if ((r >> i) & 1) { go |= bt.goth[p][i]; so ^= bt.soth[p][i]; }
-      };
-      uint64_t gthread;
-      unsigned int sthread;
-      lane_off(0, gthread, sthread);
-      {
-        double2* src = psi + gthread;
+      for (int k = 0; k < 3; ++k)
+        if ((r >> k) & 1) { go |= bt.goth[p][k]; so ^= bt.soth[p][k]; }
+    };
+    uint64_t gthread;
+    unsigned int sthread;
+    lane_off(0, base, gthread, sthread);
+    {
+      double2* src = psi + gthread;
 #pragma unroll
-        for (int b = 0; b < D; ++b) {
-          const double2 a = ld_amp(src + bt.gbits[0][b]);
-          v[b] = make_double2(g * a.x, g * a.y);    // the pending normalisation, once per pass
-        }
-      }
-      for (int p = 0; p < nphases; ++p) {
-        // gthread = physical index of this thread's group (register axes = 0), sthread = its slot base in the warp tile
-        for (int s = bt.s_begin[p]; s < bt.s_end[p]; ++s) {
-          const Stage& st = bt.st[s];
-          const unsigned int pq = __popcll(gthread & st.mq), pv = __popcll(gthread & st.mv);
-          double n0 = 0.0, n1 = 0.0;
-          const int la = bt.lax[s];
-          if (la == 0) stage_on_axis<R, 0>(v, st, pq, pv, n0, n1);
-          else if (la == 1) stage_on_axis<R, 1>(v, st, pq, pv, n0, n1);
-          else if (R == 3 || la == 2) stage_on_axis<R, 2>(v, st, pq, pv, n0, n1);
-          else stage_on_axis<R, R - 1>(v, st, pq, pv, n0, n1);
-          if (st.acc) sacc[s][tid] += n0 + n1;
-        }
-        if (p + 1 < nphases) {
-          // transpose through the warp's private tile to the register assignment of the next phase
-          const unsigned int s_old = sthread;
-          lane_off(p + 1, gthread, sthread);
-          const unsigned int s_new = sthread;
-          __syncwarp();                             // every lane has read its slots of the previous transpose
-#pragma unroll
-          for (int b = 0; b < D; ++b) tile[s_old ^ bt.sbits[p][b]] = v[b];
-          __syncwarp();
-#pragma unroll
-          for (int b = 0; b < D; ++b) v[b] = tile[s_new ^ bt.sbits[p + 1][b]];
-        } else {
-          double2* dst = psi + gthread;
-#pragma unroll
-          for (int b = 0; b < D; ++b) st_amp(dst + bt.gbits[p][b], v[b]);
-        }
+      for (int b = 0; b < D; ++b) {
+        const double2 a = ld_amp(src + bt.gbits[0][b]);
+        v[b] = make_double2(g * a.x, g * a.y);    // the pending normalisation, once per pass
       }
     }
+    // The warp's NEXT tile is asked into L2 now: a warp computes on its tile for thousands of cycles with its 2^R loads
+    // long retired, so without this only the warps that happen to sit in their load phase keep HBM busy (ncu, config 2:
+    // long-scoreboard stalls = a quarter of the warp time).  One request per 128-byte line; the index expansion is
+    // the one the next iteration needs anyway.
+    const uint64_t tn = tile_of(++i);
+    if (tn < ntiles) {
+      base_next = base_of(tn);
+      if (pf && (f & pfmask) == 0u) {
+        uint64_t gn;
+        unsigned int sn;
+        lane_off(0, base_next, gn, sn);
+        const double2* nsrc = psi + gn;
+#pragma unroll
+        for (int b = 0; b < D; ++b) prefetch_l2(nsrc + bt.gbits[0][b]);
+      }
+    }
+    for (int p = 0; p < nphases; ++p) {
+      // gthread = physical index of this thread's group (register axes = 0), sthread = its slot base in the warp tile
+      for (int s = bt.s_begin[p]; s < bt.s_end[p]; ++s) {
+        const Stage& st = bt.st[s];
+        double n0 = 0.0, n1 = 0.0;
+        const int la = bt.lax[s];
+        if (la == 0) stage_on_axis<R, 0>(v, st, gthread, n0, n1);
+        else if (la == 1) stage_on_axis<R, 1>(v, st, gthread, n0, n1);
+        else if (R == 3 || la == 2) stage_on_axis<R, 2>(v, st, gthread, n0, n1);
+        else stage_on_axis<R, R - 1>(v, st, gthread, n0, n1);
+        if (st.acc) sacc[s][tid] += n0 + n1;
+      }
+      if (p + 1 < nphases) {
+        // transpose through the warp's private tile to the register assignment of the next phase
+        const unsigned int s_old = sthread;
+        lane_off(p + 1, base, gthread, sthread);
+        const unsigned int s_new = sthread;
+        __syncwarp();                             // every lane has read its slots of the previous transpose
+#pragma unroll
+        for (int b = 0; b < D; ++b) tile[s_old ^ bt.sbits[p][b]] = v[b];
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < D; ++b) v[b] = tile[s_new ^ bt.sbits[p + 1][b]];
+      } else {
+        double2* dst = psi + gthread;
+#pragma unroll
+        for (int b = 0; b < D; ++b) st_amp(dst + bt.gbits[p][b], v[b]);
+      }
+    }
+    t = tn;
   }
   double acc[MAX_STAGES];
 #pragma unroll
@@ -796,12 +835,11 @@ __global__ void __launch_bounds__(TPB, 2) k_fused_tma(double2* __restrict__ psi,
       }
       for (int s = bt.s_begin[p]; s < bt.s_end[p]; ++s) {
         const Stage& st = bt.st[s];
-        const unsigned int pq = __popcll(gthread & st.mq), pv = __popcll(gthread & st.mv);
         double n0 = 0.0, n1 = 0.0;
         const int la = bt.lax[s];
-        if (la == 0) stage_on_axis<3, 0>(v, st, pq, pv, n0, n1);
-        else if (la == 1) stage_on_axis<3, 1>(v, st, pq, pv, n0, n1);
-        else stage_on_axis<3, 2>(v, st, pq, pv, n0, n1);
+        if (la == 0) stage_on_axis<3, 0>(v, st, gthread, n0, n1);
+        else if (la == 1) stage_on_axis<3, 1>(v, st, gthread, n0, n1);
+        else stage_on_axis<3, 2>(v, st, gthread, n0, n1);
         if (st.acc) sacc[s][tid] += n0 + n1;
       }
 #pragma unroll

@@ -62,9 +62,14 @@ enum {
                             * mbarrier) whenever the layout allows; 0 (default) = register-staged kernels */
   GXSV_OPT_TILE_REGS = 9,  /* tuning: register axes per phase of the multi-axis batched pass: 3 (2^3 amplitudes per thread,
                             * 4 CTAs per SM) or 4 (default: 2^4 per thread, 2 CTAs per SM, fewer phases) */
-  GXSV_OPT_DIST_QUEUE = 10 /* sharded STRICT mode: 1 = projections whose outcome probability is analytic are queued like in
+  GXSV_OPT_DIST_QUEUE = 10,/* sharded STRICT mode: 1 = projections whose outcome probability is analytic are queued like in
                             * the single-GPU strict mode (gxsv_project_qubit then returns NaN norms and the caller collects
                             * them later with gxsv_take_norms); everything else still returns its local half-norms at once */
+  GXSV_OPT_TILE_PREFETCH = 11, /* tuning: 1 = the multi-axis batched pass asks every warp's next tile into L2
+                            * (prefetch.global.L2) while the current one is computed; 0 (default): measured faster */
+  GXSV_OPT_DEFER_VCZ = 12  /* tuning: 1 (default) = a queued projection leaves the CZs of the newly materialised partner
+                            * queued (they are applied, for free, by the projection that measures one of their ends);
+                            * 0 = they are applied as signs inside the stage that materialises the partner */
 };
 
 /* kernel kinds reported by gxsv_profile_read / gxsv_stats */

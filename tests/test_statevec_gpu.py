@@ -474,6 +474,69 @@ def test_batched_passes_on_many_axes_against_oracle(n, axes, glog, tma):
         assert passes <= 16          # 48 stages: at least three per pass on average
 
 
+@pytest.mark.parametrize("defer,prefetch", [(1, 1), (0, 1), (1, 0)])
+@pytest.mark.parametrize("axes,batch,glog", [(7, 12, 0), (7, 12, 2), (6, 12, 1), (4, 12, 0), (3, 12, 0)])
+@pytest.mark.parametrize("n", [14, 17, 20])
+def test_twelve_stage_passes_deferred_partner_cz_and_prefetch(n, axes, batch, glog, defer, prefetch):
+    """The bench-default pass shape (up to 12 stages on up to 7 axes, 2^4 amplitudes per thread) against the oracle, with
+    the round-2 kernel variants switched both ways: partner CZs left queued (GXSV_OPT_DEFER_VCZ, the default) or applied
+    as signs inside the stage, next-tile L2 prefetch on / off.  Mostly |+> partners and XY-plane measurements, as in
+    transpiled patterns (the 6-FMA butterfly with per-pair and thread-uniform signs), mixed with |-> / planar partners and
+    arbitrary measurement axes (the general stages); CZs hang on both the measured and the new qubit, and some
+    measured qubits are the partners of earlier stages of the same pass (their deferred CZs come back as that stage's
+    own signs)."""
+    from graphix_b200 import _lib
+
+    rng = np.random.default_rng(7000 * n + 100 * axes + 10 * glog + 2 * defer + prefetch)
+    psi = rand_state(rng, n)
+    dev = _sv(psi, n + 1, fusion=2, strict=False, batch=batch)
+    dev.set_option(_lib.OPT_BATCH_AXES, axes)
+    dev.set_option(_lib.OPT_CHUNK_LOG2, glog)
+    dev.set_option(_lib.OPT_TILE_REGS, 4)
+    dev.set_option(_lib.OPT_DEFER_VCZ, defer)
+    dev.set_option(_lib.OPT_TILE_PREFETCH, prefetch)
+    orc = OracleStatevector(psi, max_qubits=n + 1)
+    npass0 = dev.stats()["fused"]["launches"]
+    last_new = None
+    for step in range(60):
+        # every third stage measures the qubit the previous stage created (same physical bit: axis reuse)
+        if last_new is not None and step % 3 == 1:
+            m = last_new
+        else:
+            m = int(rng.integers(n))
+        others = [int(x) for x in rng.choice([i for i in range(n) if i != m], size=3, replace=False)]
+        kind = int(rng.integers(8))
+        st = [mbqc.BasicStates.PLUS] * 5 + [mbqc.BasicStates.MINUS, mbqc.PlanarState(mbqc.Plane.XY, 0.3),
+                                            mbqc.PlanarState(mbqc.Plane.YZ, 0.7)]
+        st = st[kind]
+        if step % 4 == 3:
+            vec = rng.normal(size=3)
+            vec /= np.linalg.norm(vec)
+        else:
+            ang = float(rng.uniform(0, 2 * np.pi))
+            vec = np.array([np.cos(ang), np.sin(ang), 0.0])
+        pm = outcome_to_operator_matrix(vec, int(rng.integers(2)))
+        for s in (dev, orc):
+            s.add_nodes(1, st)
+            s.entangle((n, m))
+            if step % 2 == 0:
+                s.entangle((m, others[0]))
+            if step % 3 != 2:
+                s.entangle((n, others[1]))
+            if step % 5 == 0:
+                s.entangle((n, others[2]))
+            s.project_qubit(pm, m)
+        # the new qubit sits at logical index n - 1 after the measured one was removed
+        last_new = n - 1
+        if step % 20 == 19:
+            np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
+    np.testing.assert_allclose(dev.flatten(), orc.flatten(), atol=1e-11)
+    assert abs(dev.norm2() - 1) < 1e-12
+    passes = dev.stats()["fused"]["launches"] - npass0
+    if axes >= 6:
+        assert passes <= 20          # 60 stages: at least three per pass on average
+
+
 def test_read_outs_on_the_device():
     """Sparse to_dict / to_prob_dict (statevec.py:591-678) compacted on the device, the in-place inner product behind
     fidelity / expectation_value with two DIFFERENT physical layouts, entangle(q, q), and the clone."""

@@ -33,12 +33,13 @@ def main():
     rows = []
     hi = n - 1
 
-    def run(label, axes, stages, batch_axes, glog, tma=int(os.environ.get("MB_TMA", "1"))):
+    def run(label, axes, stages, batch_axes, glog, tma=int(os.environ.get("MB_TMA", "0")), prefetch=1):
         sv.set_option(_lib.OPT_TMA, tma)
+        sv.set_option(_lib.OPT_TILE_PREFETCH, prefetch)
         sv.set_option(_lib.OPT_TILE_REGS, int(os.environ.get("MB_TILE_REGS", "4")))
         sv.set_option(_lib.OPT_BATCH_AXES, batch_axes)
         sv.set_option(_lib.OPT_CHUNK_LOG2, glog)
-        sv.set_option(_lib.OPT_BATCH, min(8, stages))
+        sv.set_option(_lib.OPT_BATCH, min(12, stages))
         for timed in (False, True):
             sv.sync()
             sv.reset_stats()
@@ -54,7 +55,7 @@ def main():
         st = sv.stats()["fused"]
         ms = st["device_ms"] / max(st["launches"], 1)
         gbs = st["algo_bytes"] / (st["device_ms"] * 1e-3) / 1e9 if st["device_ms"] else 0.0
-        rows.append({"n": n, "case": label, "axes": list(axes), "stages": stages, "batch_axes": batch_axes, "glog": glog,
+        rows.append({"n": n, "case": label, "prefetch": prefetch, "axes": list(axes), "stages": stages, "batch_axes": batch_axes, "glog": glog,
                      "launches": st["launches"], "ms_per_pass": ms, "algo_GBps": gbs})
         print(f"n={n} {label:28s} axes={str(list(axes)):26s} stages={stages} A<={batch_axes} glog={glog}: "
               f"{st['launches']:3d} passes {ms:9.4f} ms  {gbs:7.1f} GB/s", flush=True)
@@ -81,6 +82,19 @@ def main():
     run("5 axes spread via A<=3", five_spread, 8, 3, 3)
     run("5 axes incl. low bits", (1, 4, n // 2, hi - 3, hi), 8, 5, 3)
     run("3 axes, 8 stages", spread, 8, 3, 3)
+    # 4) the shape the QAOA / QFT patterns fill their passes with: 12 stages on 7 axes (3 phases), and the L2 prefetch
+    seven = (8, 11, 12, n // 2, hi - 5, hi - 2, hi)
+    seven_top = tuple(range(hi - 6, hi + 1))
+    quick = os.environ.get("MB_QUICK", "0") == "1"
+    for pfx in ((0,) if quick else (1, 0)):
+        for glog in (0, 1, 3, 5):
+            run("7 axes spread, 12 stages", seven, 12, 7, glog, prefetch=pfx)
+            run("7 axes top, 12 stages", seven_top, 12, 7, glog, prefetch=pfx)
+            run("5 axes top, 8 stages", five_top, 8, 5, glog, prefetch=pfx)
+        run("5 axes spread, 8 stages", five_spread, 8, 5, 3, prefetch=pfx)
+        run("4 axes spread, 12 stages", (9, n // 2, hi - 2, hi), 12, 4, 3, prefetch=pfx)
+        run("6 axes top, 12 stages", tuple(range(hi - 5, hi + 1)), 12, 6, 0, prefetch=pfx)
+        run("6 axes top, 12 stages", tuple(range(hi - 5, hi + 1)), 12, 6, 3, prefetch=pfx)
     print("norm2", sv.norm2())
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/microbench_batch_{n}.json", "w") as f:
