@@ -12,7 +12,7 @@ from . import _build
 
 GXSV_OK, GXSV_EINDEX, GXSV_EVALUE, GXSV_EZERONORM, GXSV_ECUDA, GXSV_ENOMEM, GXSV_EUNSUPPORTED = range(7)
 OPT_FUSION, OPT_STRICT, OPT_PROFILE, OPT_DIST, OPT_BATCH, OPT_BATCH_AXES, OPT_CHUNK_LOG2, OPT_TMA, OPT_TILE_REGS, OPT_DIST_QUEUE = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
-OPT_TILE_PREFETCH, OPT_DEFER_VCZ = 11, 12
+OPT_TILE_PREFETCH, OPT_DEFER_VCZ, OPT_TILE_WARPS = 11, 12, 13
 KIND_NAMES = ("fill", "cz", "contract", "apply1q", "expect", "gather", "fused", "tensor", "misc")
 K_COUNT = len(KIND_NAMES)
 

@@ -102,6 +102,8 @@ struct gxsv {
   int analytic_norms = 1;  // skip the norm accumulation of stages whose outcome probability is known to be 1/2
   int use_tma = 0;         // 1: batched passes stage CTA tiles through shared memory with bulk copies (k_fused_tma; measured slower for many
                            // stages per pass, see kernels.cuh) when the layout allows
+  int stage_prefetch = 1;         // k_fused_tile fetches the operands of stage s + 1 from shared memory while stage s runs (GXSV_STAGE_PREFETCH)
+  int tile_warps = 0;             // warps sharing one tile of k_fused_tile: 0 = by the number of axes, else 1 / 4 / 8 (GXSV_TILE_WARPS)
   int tile_prefetch = 0;          // 1: k_fused_tile asks its next warp tile into L2 (GXSV_TILE_PREFETCH=1; measured slower: 42.1 k
                                   // against 49.5 k commands/s on config 2, 4.0 k against 5.3 k on config 3 — kept as an option)
   bool defer_partner_cz = true;   // batched stages leave the partner's CZs queued (GXSV_DEFER_VCZ=0: apply them in the stage)
@@ -290,12 +292,12 @@ unsigned long long parity_table(uint64_t mask, const unsigned char* regbit, int 
 // acts on at most three distinct batch axes (those are held in registers, k_fused_tile).  Returns the number of
 // phases (out may be NULL: the queueing code only asks whether one more stage still fits MAX_PHASES).  With `out`,
 // also tabulates the offsets the kernel addresses with.
-int plan_phases(const Batch& bt, TileBatch* out, int R) {
+int plan_phases(const Batch& bt, TileBatch* out, int R, int tile_log2 = 0) {
   // XOR swizzle of a shared-memory slot index (see k_fused_tile): bit 2 ^= parity of the bits above it
   auto sw = [](unsigned int x) { return x ^ ((unsigned int)(__builtin_popcount(x >> 3) & 1) << 2); };
   int nph = 0;
   int i = 0;
-  const int A = bt.naxes, F = (5 + R) - A;
+  const int A = bt.naxes, F = (tile_log2 ? tile_log2 : 5 + R) - A;   // consecutive amplitudes per axis combination of a tile
   while (i < bt.nstages) {
     int T[4], nt = 0, j = i;
     for (; j < bt.nstages; ++j) {
@@ -492,14 +494,35 @@ int flush_batch(gxsv_t* h) {
     tb.naxes = bt.naxes;
     for (int k = 0; k < bt.nstages; ++k) { tb.st[k] = bt.st[k]; tb.nscale[k] = bt.nscale[k]; }
     const int R = h->tile_regs;
-    tb.nphases = plan_phases(bt, &tb, R);
+    // warps per tile: private warp tiles while the runs stay >= 256 bytes (up to 5 axes at R = 4), else four warps share
+    // a tile (runs of 2^(7 + R - A) amplitudes); GXSV_TILE_WARPS / GXSV_OPT_TILE_WARPS override (1, 4 or 8)
+    int TW = h->tile_warps;
+    if (TW == 0) TW = (bt.naxes >= R + 2) ? 4 : 1;
+    if (R == 3) TW = 1;
+    const int ltw = (TW == 8) ? 3 : (TW == 4) ? 2 : 0;
+    tb.nphases = plan_phases(bt, &tb, R, 5 + R + ltw);
+    for (int k = 0; k < bt.nstages; ++k) {      // dispatch codes and packed operands of the stages (stage_by_variant)
+      const Stage& st = tb.st[k];
+      unsigned int variant;
+      if (st.kind == 0 && st.mv == 0ull && !st.neg) variant = st.acc ? SV_FAST_ACC : (st.qtab == 0ull ? SV_UNIQ : SV_FAST);
+      else variant = (st.kind == 0) ? SV_K0_SIGNED : (st.kind == 1) ? SV_K1 : SV_GENERAL;
+      tb.code[k] = (unsigned char)(32u * tb.lax[k] + (st.acc ? 16u : 0u) + variant);
+      tb.hot[k].a = st.a;
+      tb.hot[k].qtab = st.qtab;
+      tb.hot[k].mq = st.mq;
+    }
     tb.prefetch = h->tile_prefetch;
     if (tb.nphases > MAX_PHASES) return fail(h, GXSV_EVALUE, "internal: batch needs %d phases", tb.nphases);
     const uint64_t ntiles = 1ull << (n - (8 + R));            // CTA iterations: 8 warp tiles of 2^(5+R) amplitudes
     const size_t dyn = sizeof(double2) << (8 + R);
     if (!h->attr_tile) {     // per handle: function attributes belong to the device context
-      CU(cudaFuncSetAttribute(k_fused_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 11)));
-      CU(cudaFuncSetAttribute(k_fused_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 12)));
+      const int dyn11 = (int)(sizeof(double2) << 11), dyn12 = (int)(sizeof(double2) << 12);
+      CU(cudaFuncSetAttribute(k_fused_tile<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn11));
+      CU(cudaFuncSetAttribute(k_fused_tile<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn12));
+      CU(cudaFuncSetAttribute(k_fused_tile<4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn12));
+      CU(cudaFuncSetAttribute(k_fused_tile<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn12));
+      CU(cudaFuncSetAttribute(k_fused_tile<4, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn12));
+      CU(cudaFuncSetAttribute(k_fused_tile<4, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn12));
       h->attr_tile = true;
     }
     uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * (R == 3 ? 4 : 2));   // persistent: resident CTAs only
@@ -513,8 +536,16 @@ int flush_batch(gxsv_t* h) {
       for (int a = 0; a < bt.naxes; ++a) fprintf(stderr, "%d%s", (int)bt.axbit[a], a + 1 < bt.naxes ? "," : "\n");
     }
     Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n), /*frame_aware=*/true);   // a pending frame was issued AFTER these stages
-    if (R == 3) k_fused_tile<3><<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm);
-    else k_fused_tile<4><<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm);
+#define GXSV_TILE_LAUNCH(RR, WW, SS) \
+  k_fused_tile<RR, WW, SS><<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm)
+    const bool sp = h->stage_prefetch != 0;
+    if (R == 3) GXSV_TILE_LAUNCH(3, 1, false);
+    else if (TW == 8) GXSV_TILE_LAUNCH(4, 8, true);
+    else if (TW == 4 && sp) GXSV_TILE_LAUNCH(4, 4, true);
+    else if (TW == 4) GXSV_TILE_LAUNCH(4, 4, false);
+    else if (sp) GXSV_TILE_LAUNCH(4, 1, true);
+    else GXSV_TILE_LAUNCH(4, 1, false);
+#undef GXSV_TILE_LAUNCH
   }
   Deferred d;
   d.first = seq;
@@ -918,6 +949,8 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
   if (const char* tm = std::getenv("GXSV_TMA")) h->use_tma = std::atoi(tm) ? 1 : 0;
   if (const char* mp = std::getenv("GXSV_MAX_PHASES")) { const int v = std::atoi(mp); if (v >= 1 && v <= MAX_PHASES) h->max_phases = v; }
   if (const char* lf = std::getenv("GXSV_LAZY_FRAME")) h->lazy_frame = std::atoi(lf) != 0;
+  if (const char* sp = std::getenv("GXSV_STAGE_PREFETCH")) h->stage_prefetch = std::atoi(sp) != 0;
+  if (const char* tw = std::getenv("GXSV_TILE_WARPS")) { const int v = std::atoi(tw); if (v == 0 || v == 1 || v == 4 || v == 8) h->tile_warps = v; }
   if (const char* tp = std::getenv("GXSV_TILE_PREFETCH")) h->tile_prefetch = std::atoi(tp) != 0;
   if (const char* dv = std::getenv("GXSV_DEFER_VCZ")) h->defer_partner_cz = std::atoi(dv) != 0;
   if (const char* tr = std::getenv("GXSV_TILE_REGS")) h->tile_regs = (std::atoi(tr) == 3) ? 3 : 4;
@@ -1049,6 +1082,10 @@ int gxsv_set_option(gxsv_t* h, int key, int value) {
     case GXSV_OPT_TILE_PREFETCH:
       h->tile_prefetch = value ? 1 : 0;
       return GXSV_OK;
+    case GXSV_OPT_TILE_WARPS:
+      if (value != 0 && value != 1 && value != 4 && value != 8) return fail(h, GXSV_EVALUE, "warps per tile must be 0 (auto), 1, 4 or 8");
+      h->tile_warps = value;
+      return GXSV_OK;
     case GXSV_OPT_DEFER_VCZ:
       h->defer_partner_cz = value != 0;
       return GXSV_OK;
@@ -1074,6 +1111,7 @@ int gxsv_get_option(gxsv_t* h, int key, int* value) {
     case GXSV_OPT_TILE_REGS: *value = h->tile_regs; return GXSV_OK;
     case GXSV_OPT_DIST_QUEUE: *value = h->dist_queue; return GXSV_OK;
     case GXSV_OPT_TILE_PREFETCH: *value = h->tile_prefetch; return GXSV_OK;
+    case GXSV_OPT_TILE_WARPS: *value = h->tile_warps; return GXSV_OK;
     case GXSV_OPT_DEFER_VCZ: *value = h->defer_partner_cz ? 1 : 0; return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
   }

@@ -68,6 +68,7 @@ __device__ __forceinline__ double2 cmad2(const double2 a, const double2 x, const
 __device__ __forceinline__ double cnorm2(const double2 a) { return fma(a.x, a.x, a.y * a.y); }
 
 // streaming accesses: the state is touched once per pass and is far larger than L2
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ double2 ld_amp(const double2* p) { return __ldcs(p); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p))); }
 __device__ __forceinline__ void st_amp(double2* p, const double2 v) { __stcs(p, v); }
@@ -437,9 +438,8 @@ __device__ __forceinline__ double flip_sign(const double x, const unsigned int s
 // UNIQ (kind 0 only): no CZ partner of the measured qubit sits on another register axis, so the sign of t1 is the same
 // for all pairs of the thread and is folded into the multiplier once (no per-pair sign work at all: 6 DFMA per pair).
 template <int NB, int AX, int KIND, bool ACC, bool HASV, bool UNIQ = false>
-__device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& st, const unsigned long long tq64,
+__device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& st, double2 a, const unsigned long long tq64,
                                             const unsigned long long tv64, double& nrm0, double& nrm1) {
-  double2 a = st.a;
   if (UNIQ) {
     const unsigned int s = __byte_perm((unsigned int)tq64, 0u, 0x0444);
     a.x = flip_sign(a.x, s);
@@ -499,16 +499,41 @@ __device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage
   const unsigned int gpar_q = __popcll(gfixed & st.mq);
   const unsigned long long tq = st.qtab ^ ((gpar_q & 1u) ? 0x8080808080808080ull : 0ull);
   if (st.kind == 0 && st.mv == 0ull && !st.neg) {          // every stage of a transpiled pattern
-    if (st.acc) stage_pairs<NB, AX, 0, true, false>(v, st, tq, 0ull, nrm0, nrm1);
-    else if (st.qtab == 0ull) stage_pairs<NB, AX, 0, false, false, true>(v, st, tq, 0ull, nrm0, nrm1);
-    else stage_pairs<NB, AX, 0, false, false>(v, st, tq, 0ull, nrm0, nrm1);
+    if (st.acc) stage_pairs<NB, AX, 0, true, false>(v, st, st.a, tq, 0ull, nrm0, nrm1);
+    else if (st.qtab == 0ull) stage_pairs<NB, AX, 0, false, false, true>(v, st, st.a, tq, 0ull, nrm0, nrm1);
+    else stage_pairs<NB, AX, 0, false, false>(v, st, st.a, tq, 0ull, nrm0, nrm1);
     return;
   }
   const unsigned int gpar_v = __popcll(gfixed & st.mv);
   const unsigned long long tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x8080808080808080ull : 0ull);
-  if (st.kind == 0) stage_pairs<NB, AX, 0, true, true>(v, st, tq, tv, nrm0, nrm1);
-  else if (st.kind == 1) stage_pairs<NB, AX, 1, true, true>(v, st, tq, tv, nrm0, nrm1);
-  else stage_pairs<NB, AX, 2, true, true>(v, st, tq, tv, nrm0, nrm1);
+  if (st.kind == 0) stage_pairs<NB, AX, 0, true, true>(v, st, st.a, tq, tv, nrm0, nrm1);
+  else if (st.kind == 1) stage_pairs<NB, AX, 1, true, true>(v, st, st.a, tq, tv, nrm0, nrm1);
+  else stage_pairs<NB, AX, 2, true, true>(v, st, st.a, tq, tv, nrm0, nrm1);
+}
+
+// The same dispatch driven by ONE host-made code per stage (tile kernel): register axis, variant and the accumulate
+// flag in one byte (TileBatch::code), and
+// the three operands every common variant needs (multiplier, sign table, sign mask) come from a packed table that the
+// caller fetches one stage ahead.  Without it a stage began with a chain of five dependent constant loads (register
+// axis -> kind -> flags -> table -> multiplier), each an indexed LDC round trip with only four warps per scheduler
+// to hide it (ncu, config 3: short-scoreboard stalls 1.9 - 3.3 per issued instruction).
+enum : unsigned int { SV_UNIQ = 0, SV_FAST = 1, SV_FAST_ACC = 2, SV_K0_SIGNED = 3, SV_K1 = 4, SV_GENERAL = 5 };
+struct StageHot {
+  double2 a;                    // Stage::a
+  unsigned long long qtab, mq;  // Stage::qtab, Stage::mq
+};
+template <int NB, int AX>
+__device__ __forceinline__ void stage_by_variant(double2 (&v)[1 << NB], const unsigned int variant, const Stage& st,
+                                                 const double2 a, const unsigned long long tq, const uint64_t gfixed,
+                                                 double& nrm0, double& nrm1) {
+  if (variant == SV_UNIQ) return stage_pairs<NB, AX, 0, false, false, true>(v, st, a, tq, 0ull, nrm0, nrm1);
+  if (variant == SV_FAST) return stage_pairs<NB, AX, 0, false, false>(v, st, a, tq, 0ull, nrm0, nrm1);
+  if (variant == SV_FAST_ACC) return stage_pairs<NB, AX, 0, true, false>(v, st, a, tq, 0ull, nrm0, nrm1);
+  const unsigned int gpar_v = __popcll(gfixed & st.mv);
+  const unsigned long long tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x8080808080808080ull : 0ull);
+  if (variant == SV_K0_SIGNED) stage_pairs<NB, AX, 0, true, true>(v, st, a, tq, tv, nrm0, nrm1);
+  else if (variant == SV_K1) stage_pairs<NB, AX, 1, true, true>(v, st, a, tq, tv, nrm0, nrm1);
+  else stage_pairs<NB, AX, 2, true, true>(v, st, a, tq, tv, nrm0, nrm1);
 }
 
 // Batch on at most three physical bits: a thread owns the 2^A amplitudes of one group in registers and applies the
@@ -590,6 +615,8 @@ struct TileBatch {
   int prefetch;                               // != 0: ask the next warp tile into L2 while the current one is computed
   unsigned char lax[MAX_STAGES];              // register slot (0..R-1) of the axis of every stage inside its phase
   unsigned char s_begin[MAX_PHASES], s_end[MAX_PHASES];
+  unsigned char code[MAX_STAGES + 4];         // 32 * lax + 16 * (accumulate the norm) + variant (SV_*), see stage_by_variant
+  StageHot hot[MAX_STAGES + 1];               // the operands of the common variants, packed (one spare entry: fetched ahead)
   // everything a thread needs to address its 2^R amplitudes is tabulated by the host (no per-tile index arithmetic):
   unsigned long long gbits[MAX_PHASES][16];   // physical offset of register slot b in phase p
   unsigned long long goth[MAX_PHASES][4];     // physical offset of the i-th axis fixed per lane (taken iff bit i of r = lane >> F)
@@ -598,29 +625,68 @@ struct TileBatch {
   double nscale[MAX_STAGES];
   Stage st[MAX_STAGES];
 };
-// R = register axes per phase: 3 (2^3 amplitudes per thread, 64 registers, 4 CTAs per SM, warp tile 2^8) or 4 (2^4
-// amplitudes per thread, 128 registers, 2 CTAs per SM, warp tile 2^9: fewer phases, runs twice as long).
-template <int R>
+// R = register axes per phase: 3 (2^3 amplitudes per thread, 64 registers, 4 CTAs per SM) or 4 (2^4 amplitudes per
+// thread, 128 registers, 2 CTAs per SM: fewer phases, runs twice as long).
+// TW = warps that share one tile (1, 4 or 8): a tile is 2^A axis combinations x 2^F consecutive amplitudes with
+// F = 5 + R + log2(TW) - A, so a pass on 7 axes reads runs of 64 bytes with private warp tiles (TW = 1) — measured
+// at 27 qubits: 0.58 of the copy rate against 0.87 for the 256-byte runs of a 5-axis pass, and 1.8 ms against 1.1 ms
+// when the seven axes are the top bits instead of spread — but runs of 256 / 512 bytes when four / eight warps share
+// the tile.  The group then transposes through its shared tile behind a named barrier (bar.sync on 32 TW threads)
+// instead of __syncwarp; groups of one CTA and the CTAs of an SM stay independent of each other.
+// SP = the stage operands are staged in shared memory and fetched one stage ahead by asm-volatile loads (which neither
+// the compiler nor ptxas sinks to the first use); SP = false reads them from the kernel parameters, where the fetch of
+// stage s + 1 ends up at the bottom of stage s whatever the source order.
+template <int R, int TW, bool SP>
 __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* __restrict__ psi, const __grid_constant__ Holes hs,
                                                       const __grid_constant__ TileBatch bt, const uint64_t ntiles,
                                                       const int glog, double* __restrict__ partials, Ctrl* ctrl,
                                                       Res* res, const unsigned long long seq, const int fin_mode) {
-  constexpr int WT = 5 + R;                         // log2 amplitudes per warp tile
+  constexpr int LTW = (TW == 1) ? 0 : (TW == 2) ? 1 : (TW == 4) ? 2 : 3;
+  constexpr int WT = 5 + R + LTW;                   // log2 amplitudes per group tile
+  constexpr int GT = 32 * TW;                       // threads per group
+  constexpr int NG = TPB / GT;                      // groups per CTA
+  static_assert(NG == 1 || NG == 2 || TW == 1, "named barriers are written out for two groups");
   constexpr int D = 1 << R;
-  extern __shared__ double2 tile_all[];             // 8 warps x 2^WT amplitudes (dynamic)
+  extern __shared__ double2 tile_all[];             // NG groups x 2^WT amplitudes (dynamic) = 2^(8+R) amplitudes per CTA
   __shared__ double sacc[MAX_STAGES][TPB];
   const int F = WT - bt.naxes;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double2* tile = tile_all + ((size_t)warp << WT);
-  const unsigned int f = lane & ((1u << F) - 1u);
+  const int tid = threadIdx.x, tg = tid & (GT - 1), grp = tid / GT;
+  double2* tile = tile_all + ((size_t)grp << WT);
+  auto group_sync = [&]() {
+    if (TW == 1) __syncwarp();
+    else if (NG == 1) __syncthreads();
+    else if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory");   // immediate ids: a register id makes
+    else asm volatile("bar.sync 2, %0;" ::"n"(GT) : "memory");                  // ptxas reserve all 16 barriers
+  };
+  const unsigned int f = tg & ((1u << F) - 1u);
   // shared-memory slots are XOR-swizzled: bit 2 of the slot index ^= parity of the bits above it, so that the 8 lanes of
   // a quarter warp (one 128-byte wavefront of 16-byte accesses) always hit 8 different bank groups — without it passes on
   // 7 axes (F = 2) ran with 2-way conflicts on every transpose (ncu: 53 % of the shared wavefronts).  The swizzle is
   // linear over XOR and the parts of an index occupy disjoint bits, so the host tabulates it per part.
   const unsigned int fsw = f ^ ((__popc(f >> 3) & 1u) << 2);
-  const int r = lane >> F;
+  const int r = tg >> F;
   const double g = ctrl->g;
   const int nphases = bt.nphases;
+  __shared__ __align__(16) StageHot shot[MAX_STAGES + 1];
+  __shared__ unsigned int scode[MAX_STAGES + 4];
+  if (SP) {
+    if (tid <= MAX_STAGES) { shot[tid] = bt.hot[tid]; scode[tid] = bt.code[tid]; }
+    __syncthreads();
+  }
+  // operands of stage k (SP: from shared memory, pinned where it is written)
+  auto fetch = [&](int k, unsigned int& c, double2& am, unsigned long long& qt, unsigned long long& m) {
+    if (SP) {
+      const unsigned int ha = smem_u32(&shot[k]), ca = smem_u32(&scode[k]);
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(am.x), "=d"(am.y) : "r"(ha));
+      asm volatile("ld.shared.v2.u64 {%0, %1}, [%2+16];" : "=l"(qt), "=l"(m) : "r"(ha));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(ca));
+    } else {
+      c = bt.code[k];
+      am = bt.hot[k].a;
+      qt = bt.hot[k].qtab;
+      m = bt.hot[k].mq;
+    }
+  };
   const bool pf = bt.prefetch != 0;
   const unsigned int pfmask = (F >= 3) ? 7u : ((1u << F) - 1u);   // lanes that start a 128-byte line (or a shorter run)
 #pragma unroll
@@ -628,7 +694,7 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
   // the i-th CTA tile of this CTA: chunks of 2^glog consecutive tiles, chunks dealt round robin (monotonic in i)
   const uint64_t gmask = (1ull << glog) - 1ull;
   auto tile_of = [&](uint64_t i) { return (((uint64_t)blockIdx.x + (i >> glog) * gridDim.x) << glog) + (i & gmask); };
-  auto base_of = [&](uint64_t t) { return expand(((t * (TPB / 32) + warp) << F) | f, hs); };
+  auto base_of = [&](uint64_t t) { return expand(((t * NG + grp) << F) | f, hs); };
   uint64_t i = 0, t = tile_of(0);
   uint64_t base_next = (t < ntiles) ? base_of(t) : 0ull;
   while (t < ntiles) {
@@ -671,27 +737,43 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
         for (int b = 0; b < D; ++b) prefetch_l2(nsrc + bt.gbits[0][b]);
       }
     }
+    // stage operands are fetched one stage ahead (s counts from 0 through the phases: uniform, so are the loads)
+    int s = 0;
+    unsigned int code;
+    double2 a;
+    unsigned long long qtab, mq;
+    fetch(0, code, a, qtab, mq);
     for (int p = 0; p < nphases; ++p) {
       // gthread = physical index of this thread's group (register axes = 0), sthread = its slot base in the warp tile
-      for (int s = bt.s_begin[p]; s < bt.s_end[p]; ++s) {
+      const int s_end = bt.s_end[p];
+      for (; s < s_end; ++s) {
+        unsigned int code_n;
+        double2 a_n;
+        unsigned long long qtab_n, mq_n;
+        fetch(s + 1, code_n, a_n, qtab_n, mq_n);
         const Stage& st = bt.st[s];
+        const unsigned long long tq = qtab ^ ((__popcll(gthread & mq) & 1) ? 0x8080808080808080ull : 0ull);
         double n0 = 0.0, n1 = 0.0;
-        const int la = bt.lax[s];
-        if (la == 0) stage_on_axis<R, 0>(v, st, gthread, n0, n1);
-        else if (la == 1) stage_on_axis<R, 1>(v, st, gthread, n0, n1);
-        else if (R == 3 || la == 2) stage_on_axis<R, 2>(v, st, gthread, n0, n1);
-        else stage_on_axis<R, R - 1>(v, st, gthread, n0, n1);
-        if (st.acc) sacc[s][tid] += n0 + n1;
+        const unsigned int la = code >> 5, variant = code & 7u;
+        if (la == 0) stage_by_variant<R, 0>(v, variant, st, a, tq, gthread, n0, n1);
+        else if (la == 1) stage_by_variant<R, 1>(v, variant, st, a, tq, gthread, n0, n1);
+        else if (R == 3 || la == 2) stage_by_variant<R, 2>(v, variant, st, a, tq, gthread, n0, n1);
+        else stage_by_variant<R, R - 1>(v, variant, st, a, tq, gthread, n0, n1);
+        if (code & 16u) sacc[s][tid] += n0 + n1;
+        code = code_n;
+        a = a_n;
+        qtab = qtab_n;
+        mq = mq_n;
       }
       if (p + 1 < nphases) {
         // transpose through the warp's private tile to the register assignment of the next phase
         const unsigned int s_old = sthread;
         lane_off(p + 1, base, gthread, sthread);
         const unsigned int s_new = sthread;
-        __syncwarp();                             // every lane has read its slots of the previous transpose
+        group_sync();                             // every thread has read its slots of the previous transpose
 #pragma unroll
         for (int b = 0; b < D; ++b) tile[s_old ^ bt.sbits[p][b]] = v[b];
-        __syncwarp();
+        group_sync();
 #pragma unroll
         for (int b = 0; b < D; ++b) v[b] = tile[s_new ^ bt.sbits[p + 1][b]];
       } else {
@@ -733,7 +815,6 @@ struct TmaBatch {
 };
 constexpr int TMA_BUFS = 3;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -67,6 +67,8 @@ enum {
                             * them later with gxsv_take_norms); everything else still returns its local half-norms at once */
   GXSV_OPT_TILE_PREFETCH = 11, /* tuning: 1 = the multi-axis batched pass asks every warp's next tile into L2
                             * (prefetch.global.L2) while the current one is computed; 0 (default): measured faster */
+  GXSV_OPT_TILE_WARPS = 13,/* tuning: warps that share one tile of the multi-axis batched pass: 0 (default) = by the number
+                            * of axes (4 from 6 axes on: runs of >= 256 bytes), 1 = private warp tiles, 4, 8 */
   GXSV_OPT_DEFER_VCZ = 12  /* tuning: 1 (default) = a queued projection leaves the CZs of the newly materialised partner
                             * queued (they are applied, for free, by the projection that measures one of their ends);
                             * 0 = they are applied as signs inside the stage that materialises the partner */

@@ -21,6 +21,24 @@ def proj(vec, r):
     return np.array([[0.5 + 0.5 * s * z, 0.5 * s * (x - 1j * y)], [0.5 * s * (x + 1j * y), 0.5 - 0.5 * s * z]])
 
 
+def sections_1_to_3(run, n, hi, lowmid, mid, top, spread, five_top, five_spread, six):
+    # 1) one stage per pass (k_fused, two streams) vs position
+    for ax in ((10,), (n // 2,), (hi,)):
+        run("1 axis, 1 stage", ax, 1, 3, 0)
+    # 2) three axes, three stages (k_fused_batch<3>, eight streams): position and chunking
+    for name, ax in (("low", lowmid), ("mid", mid), ("top", top), ("spread", spread)):
+        for glog in (3,):
+            run(f"3 axes {name}", ax, 3, 3, glog)
+    # 3) k_fused_tile: 4 / 5 / 6 axes, 8 stages
+    for name, ax in (("4 axes spread", (9, n // 2, hi - 2, hi)), ("5 axes top", five_top), ("5 axes spread", five_spread),
+                     ("6 axes", six)):
+        run(name, ax, 8, len(ax), 3)
+    # the same 8 stages on 5 axes as 3-axis passes (what round 1 ran)
+    run("5 axes spread via A<=3", five_spread, 8, 3, 3)
+    run("5 axes incl. low bits", (1, 4, n // 2, hi - 3, hi), 8, 5, 3)
+    run("3 axes, 8 stages", spread, 8, 3, 3)
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 27
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
@@ -33,8 +51,9 @@ def main():
     rows = []
     hi = n - 1
 
-    def run(label, axes, stages, batch_axes, glog, tma=int(os.environ.get("MB_TMA", "0")), prefetch=1):
+    def run(label, axes, stages, batch_axes, glog, tma=int(os.environ.get("MB_TMA", "0")), prefetch=0, tw=0):
         sv.set_option(_lib.OPT_TMA, tma)
+        sv.set_option(_lib.OPT_TILE_WARPS, tw)
         sv.set_option(_lib.OPT_TILE_PREFETCH, prefetch)
         sv.set_option(_lib.OPT_TILE_REGS, int(os.environ.get("MB_TILE_REGS", "4")))
         sv.set_option(_lib.OPT_BATCH_AXES, batch_axes)
@@ -55,46 +74,33 @@ def main():
         st = sv.stats()["fused"]
         ms = st["device_ms"] / max(st["launches"], 1)
         gbs = st["algo_bytes"] / (st["device_ms"] * 1e-3) / 1e9 if st["device_ms"] else 0.0
-        rows.append({"n": n, "case": label, "prefetch": prefetch, "axes": list(axes), "stages": stages, "batch_axes": batch_axes, "glog": glog,
+        rows.append({"n": n, "case": label, "prefetch": prefetch, "tile_warps": tw, "axes": list(axes), "stages": stages, "batch_axes": batch_axes, "glog": glog,
                      "launches": st["launches"], "ms_per_pass": ms, "algo_GBps": gbs})
-        print(f"n={n} {label:28s} axes={str(list(axes)):26s} stages={stages} A<={batch_axes} glog={glog}: "
+        print(f"n={n} {label:28s} tw={tw} axes={str(list(axes)):26s} stages={stages} A<={batch_axes} glog={glog}: "
               f"{st['launches']:3d} passes {ms:9.4f} ms  {gbs:7.1f} GB/s", flush=True)
 
     lowmid = (9, 10, 11)
     mid = (n // 2 - 1, n // 2, n // 2 + 1)
     top = (hi - 2, hi - 1, hi)
     spread = (9, n // 2, hi)
-    # 1) one stage per pass (k_fused, two streams) vs position
-    for ax in ((10,), (n // 2,), (hi,)):
-        run("1 axis, 1 stage", ax, 1, 3, 0)
-    # 2) three axes, three stages (k_fused_batch<3>, eight streams): position and chunking
-    for name, ax in (("low", lowmid), ("mid", mid), ("top", top), ("spread", spread)):
-        for glog in (3,):
-            run(f"3 axes {name}", ax, 3, 3, glog)
-    # 3) k_fused_tile: 4 / 5 / 6 axes, 8 stages
+    quick = os.environ.get("MB_QUICK", "0") == "1"
     five_top = (hi - 4, hi - 3, hi - 2, hi - 1, hi)
     five_spread = (8, 12, n // 2, hi - 3, hi)
     six = (8, 12, n // 2, hi - 5, hi - 2, hi)
-    for name, ax in (("4 axes spread", (9, n // 2, hi - 2, hi)), ("5 axes top", five_top), ("5 axes spread", five_spread),
-                     ("6 axes", six)):
-        run(name, ax, 8, len(ax), 3)
-    # the same 8 stages on 5 axes as 3-axis passes (what round 1 ran)
-    run("5 axes spread via A<=3", five_spread, 8, 3, 3)
-    run("5 axes incl. low bits", (1, 4, n // 2, hi - 3, hi), 8, 5, 3)
-    run("3 axes, 8 stages", spread, 8, 3, 3)
-    # 4) the shape the QAOA / QFT patterns fill their passes with: 12 stages on 7 axes (3 phases), and the L2 prefetch
+    if not quick:
+        sections_1_to_3(run, n, hi, lowmid, mid, top, spread, five_top, five_spread, six)
+    # 4) the shapes the QAOA / QFT / random-circuit patterns produce: 7 stages on 7 axes (2 phases), rarely 12 stages
     seven = (8, 11, 12, n // 2, hi - 5, hi - 2, hi)
     seven_top = tuple(range(hi - 6, hi + 1))
-    quick = os.environ.get("MB_QUICK", "0") == "1"
-    for pfx in ((0,) if quick else (1, 0)):
-        for glog in (0, 1, 3, 5):
-            run("7 axes spread, 12 stages", seven, 12, 7, glog, prefetch=pfx)
-            run("7 axes top, 12 stages", seven_top, 12, 7, glog, prefetch=pfx)
-            run("5 axes top, 8 stages", five_top, 8, 5, glog, prefetch=pfx)
-        run("5 axes spread, 8 stages", five_spread, 8, 5, 3, prefetch=pfx)
-        run("4 axes spread, 12 stages", (9, n // 2, hi - 2, hi), 12, 4, 3, prefetch=pfx)
-        run("6 axes top, 12 stages", tuple(range(hi - 5, hi + 1)), 12, 6, 0, prefetch=pfx)
-        run("6 axes top, 12 stages", tuple(range(hi - 5, hi + 1)), 12, 6, 3, prefetch=pfx)
+    # 5) warps per tile (run length per axis combination): private warp tiles against tiles shared by 4 / 8 warps
+    seven7 = dict(stages=7, batch_axes=7)
+    for tw in (1, 4, 8):
+        run("7 axes spread, 7 stages", seven, 7, 7, 3, tw=tw)
+        run("7 axes top, 7 stages", seven_top, 7, 7, 3, tw=tw)
+        run("7 axes spread, 12 stages", seven, 12, 7, 3, tw=tw)
+        run("6 axes, 8 stages", six, 8, 6, 3, tw=tw)
+        run("5 axes spread, 8 stages", five_spread, 8, 5, 3, tw=tw)
+        run("4 axes spread, 12 stages", (9, n // 2, hi - 2, hi), 12, 4, 3, tw=tw)
     print("norm2", sv.norm2())
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/microbench_batch_{n}.json", "w") as f:
