@@ -12,7 +12,7 @@ from . import _build
 
 GXSV_OK, GXSV_EINDEX, GXSV_EVALUE, GXSV_EZERONORM, GXSV_ECUDA, GXSV_ENOMEM, GXSV_EUNSUPPORTED = range(7)
 OPT_FUSION, OPT_STRICT, OPT_PROFILE, OPT_DIST, OPT_BATCH, OPT_BATCH_AXES, OPT_CHUNK_LOG2, OPT_TMA, OPT_TILE_REGS, OPT_DIST_QUEUE = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
-OPT_TILE_PREFETCH, OPT_DEFER_VCZ, OPT_TILE_WARPS = 11, 12, 13
+OPT_TILE_IO, OPT_DEFER_VCZ, OPT_TILE_WARPS = 11, 12, 13
 KIND_NAMES = ("fill", "cz", "contract", "apply1q", "expect", "gather", "fused", "tensor", "misc")
 K_COUNT = len(KIND_NAMES)
 
@@ -78,6 +78,8 @@ SIGNATURES = {
     "gxsv_ipc_close": (C.c_int, [_H]),
     "gxsv_swap_peer": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]),
     "gxsv_flush_batch": (C.c_int, [_H]),
+    "gxsv_plan_tile_layouts": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, _I,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gxsv_pack_half": (C.c_int, [_H, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
     "gxsv_unpack_half": (C.c_int, [_H, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_double, C.c_double]),
 }

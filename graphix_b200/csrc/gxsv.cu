@@ -104,8 +104,8 @@ struct gxsv {
                            // stages per pass, see kernels.cuh) when the layout allows
   int stage_prefetch = 1;         // k_fused_tile fetches the operands of stage s + 1 from shared memory while stage s runs (GXSV_STAGE_PREFETCH)
   int tile_warps = 0;             // warps sharing one tile of k_fused_tile: 0 = by the number of axes, else 1 / 4 / 8 (GXSV_TILE_WARPS)
-  int tile_prefetch = 0;          // 1: k_fused_tile asks its next warp tile into L2 (GXSV_TILE_PREFETCH=1; measured slower: 42.1 k
-                                  // against 49.5 k commands/s on config 2, 4.0 k against 5.3 k on config 3 — kept as an option)
+  int tile_io = 1;                // k_fused_tile: extra load / store layouts over the lowest tile bits: 0 never, 1 when three or more
+                                  // batch axes lie below bit 6 (default), 2 always (GXSV_TILE_IO)
   bool defer_partner_cz = true;   // batched stages leave the partner's CZs queued (GXSV_DEFER_VCZ=0: apply them in the stage)
   int batch_max = 0;       // > 0: queue up to this many fused projections and run them in one pass (non-strict only)
   Batch batch;             // the open batch (nstages == 0: none)
@@ -289,65 +289,155 @@ unsigned long long parity_table(uint64_t mask, const unsigned char* regbit, int 
 }
 
 // Greedy phase plan of a batch on more than three axes: every phase is the longest run of consecutive stages that
-// acts on at most three distinct batch axes (those are held in registers, k_fused_tile).  Returns the number of
-// phases (out may be NULL: the queueing code only asks whether one more stage still fits MAX_PHASES).  With `out`,
-// also tabulates the offsets the kernel addresses with.
-int plan_phases(const Batch& bt, TileBatch* out, int R, int tile_log2 = 0) {
-  // XOR swizzle of a shared-memory slot index (see k_fused_tile): bit 2 ^= parity of the bits above it
-  auto sw = [](unsigned int x) { return x ^ ((unsigned int)(__builtin_popcount(x >> 3) & 1) << 2); };
+// acts on at most R distinct batch axes (those are held in registers, k_fused_tile).  Returns the number of phases
+// (out may be NULL: the queueing code only asks whether one more stage still fits MAX_PHASES).
+// With `out` (then live_mask / tile_log2 / io_mode are needed) the LAYOUTS of the pass are tabulated (kernels.cuh,
+// k_fused_tile): the tile-index bits are the A axis bits and the F = tile_log2 - A lowest live non-axis bits; a layout
+// keeps R of them in registers and gives each of the others a bit of the thread's index in its group.
+//   * a phase keeps its (padded) axes in registers; its thread bits are ordered so that the three lowest lane bits land
+//     in different bank groups of the (XOR-folded) shared tile whenever possible;
+//   * the first / last layout is what the tile is loaded / stored in.  io_mode 1: when three or more batch axes lie
+//     below bit 6, an extra stage-less layout is put in front / at the end whose thread bits are the LOWEST tile-index
+//     bits in physical order and whose register bits are the R highest — unless the first / last phase happens to
+//     have exactly those register bits; io_mode 0: never, 2: always.
+int plan_phases(const Batch& bt, TileBatch* out, int R, uint64_t live_mask = 0, int tile_log2 = 0, int io_mode = 1) {
+  struct Phase { int T[4]; int s_begin, s_end; };
+  Phase ph[MAX_STAGES];
   int nph = 0;
   int i = 0;
-  const int A = bt.naxes, F = (tile_log2 ? tile_log2 : 5 + R) - A;   // consecutive amplitudes per axis combination of a tile
+  const int A = bt.naxes;
   while (i < bt.nstages) {
-    int T[4], nt = 0, j = i;
+    Phase& P = ph[nph];
+    int nt = 0, j = i;
     for (; j < bt.nstages; ++j) {
       const int a = bt.st[j].axis;
       bool in = false;
-      for (int k = 0; k < nt; ++k) in = in || (T[k] == a);
+      for (int k = 0; k < nt; ++k) in = in || (P.T[k] == a);
       if (in) continue;
       if (nt == R) break;
-      T[nt++] = a;
+      P.T[nt++] = a;
     }
-    if (out && nph < MAX_PHASES) {
-      // pad the register set to R axes with batch axes that the phase does not use
-      for (int a = 0; a < A && nt < R; ++a) {
-        bool in = false;
-        for (int k = 0; k < nt; ++k) in = in || (T[k] == a);
-        if (!in) T[nt++] = a;
-      }
-      std::sort(T, T + R);
-      int oth[4], no = 0;
+    // pad the register set to R axes with batch axes that the phase does not use, highest physical bits first (the
+    // best chance to coincide with the load / store layout)
+    while (nt < R) {
+      int best = -1;
       for (int a = 0; a < A; ++a) {
         bool in = false;
-        for (int k = 0; k < R; ++k) in = in || (T[k] == a);
-        if (!in) oth[no++] = a;
+        for (int k = 0; k < nt; ++k) in = in || (P.T[k] == a);
+        if (!in && (best < 0 || bt.axbit[a] > bt.axbit[best])) best = a;
       }
-      unsigned char regbit[4];
-      for (int k = 0; k < R; ++k) regbit[k] = bt.axbit[T[k]];
-      for (int b = 0; b < (1 << R); ++b) {
-        uint64_t go = 0;
-        unsigned int so = 0;
-        for (int k = 0; k < R; ++k)
-          if ((b >> k) & 1) { go |= 1ull << regbit[k]; so |= 1u << T[k]; }
-        out->gbits[nph][b] = go;
-        out->sbits[nph][b] = (unsigned short)sw(so << F);
-      }
-      for (int k = 0; k < 4; ++k) {
-        out->goth[nph][k] = (k < no) ? (1ull << bt.axbit[oth[k]]) : 0ull;
-        out->soth[nph][k] = (k < no) ? (unsigned short)sw((1u << oth[k]) << F) : (unsigned short)0;
-      }
-      out->s_begin[nph] = (unsigned char)i;
-      out->s_end[nph] = (unsigned char)j;
-      for (int s = i; s < j; ++s) {
-        int la = 0;
-        for (int k = 0; k < R; ++k) if (T[k] == bt.st[s].axis) la = k;
-        out->lax[s] = (unsigned char)la;
-        out->st[s].qtab = parity_table(bt.st[s].mq, regbit, R, la);
-        out->st[s].vtab = parity_table(bt.st[s].mv, regbit, R, la);
-      }
+      if (best < 0) break;      // fewer axes than register bits cannot happen (A >= R on this path)
+      P.T[nt++] = best;
     }
+    std::sort(P.T, P.T + nt);
+    P.s_begin = i;
+    P.s_end = j;
     nph += 1;
     i = j;
+  }
+  if (!out || nph > MAX_PHASES) return nph;
+
+  const int WT = tile_log2, F = WT - A, NTB = WT - R;
+  // tile-index bits as physical positions, ascending; canon(pos) = rank
+  int pos[16], np = 0;
+  {
+    int nf = 0;
+    for (int b = 0; b < 64 && np < WT; ++b) {
+      bool axis = false;
+      for (int a = 0; a < A; ++a) axis = axis || (bt.axbit[a] == b);
+      const bool live = (live_mask >> b) & 1ull;
+      if (axis) pos[np++] = b;
+      else if (live && nf < F) { pos[np++] = b; nf += 1; }
+      // (axes above the F-th dense bit are appended when the scan reaches them: np < WT keeps the loop going)
+    }
+  }
+  auto canon = [&](int b) { for (int k = 0; k < np; ++k) if (pos[k] == b) return k; return -1; };
+  // slot swizzle: the low three bits (16-byte bank group) are XORed with every higher 3-bit group of the slot index
+  auto sw = [](unsigned int x) { return (x & ~7u) | ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7u); };
+  struct Layout { int reg[4]; int thr[MAX_THREAD_BITS]; };
+  Layout lay[MAX_LAYOUTS];
+  int s_end[MAX_LAYOUTS];
+  int nl = 0;
+  // the I/O layout: lowest NTB tile-index bits on the threads (lane bits first), the R highest in registers
+  Layout io;
+  for (int k = 0; k < NTB; ++k) io.thr[k] = pos[k];
+  for (int k = 0; k < R; ++k) io.reg[k] = pos[NTB + k];
+  // Direct lanes run over the lowest NON-axis bits: with up to two axes below them a warp access still falls into a few
+  // 128-byte lines (measured at 27 qubits: no loss), with three or more the lanes are >= 128 bytes apart and every
+  // access touches 32 lines (config 4 at 33 live qubits: 38 - 50 ms instead of 23 ms per pass).
+  int low_axes = 0;
+  for (int a = 0; a < A; ++a) low_axes += (bt.axbit[a] < 6) ? 1 : 0;
+  const bool want_io = (io_mode == 2) || (io_mode == 1 && low_axes >= 3);
+  auto same_regs = [&](const Layout& x, const Layout& y) {
+    for (int k = 0; k < R; ++k) {
+      bool in = false;
+      for (int m = 0; m < R; ++m) in = in || (x.reg[k] == y.reg[m]);
+      if (!in) return false;
+    }
+    return true;
+  };
+  auto phase_layout = [&](const Phase& P, bool ascending) {
+    Layout L;
+    for (int k = 0; k < R; ++k) L.reg[k] = bt.axbit[P.T[k]];
+    int rest[16], nr = 0;
+    for (int k = 0; k < np; ++k) {
+      bool isreg = false;
+      for (int m = 0; m < R; ++m) isreg = isreg || (L.reg[m] == pos[k]);
+      if (!isreg) rest[nr++] = pos[k];
+    }
+    int nt = 0;
+    if (!ascending) {
+      // three lane bits with distinct canonical index mod 3 (distinct bank groups after the fold), lowest first
+      bool used_res[3] = {false, false, false};
+      bool taken[16] = {false};
+      for (int k = 0; k < nr && nt < 3; ++k) {
+        const int c = canon(rest[k]) % 3;
+        if (!used_res[c]) { used_res[c] = true; taken[k] = true; L.thr[nt++] = rest[k]; }
+      }
+      for (int k = 0; k < nr; ++k) if (!taken[k]) L.thr[nt++] = rest[k];
+    } else {
+      for (int k = 0; k < nr; ++k) L.thr[nt++] = rest[k];
+    }
+    return L;
+  };
+  for (int p = 0; p < nph; ++p) {
+    const bool io_first = want_io && p == 0, io_last = want_io && p == nph - 1;
+    // without I/O layouts a phase that the tile is loaded / stored in keeps its thread bits in physical order
+    Layout L = phase_layout(ph[p], (p == 0 || p == nph - 1) && !want_io);
+    const bool match = same_regs(L, io);
+    if ((io_first || io_last) && match) for (int k = 0; k < NTB; ++k) L.thr[k] = io.thr[k];   // the phase IS the I/O layout
+    if (io_first && !match) { lay[nl] = io; s_end[nl] = 0; nl += 1; }
+    lay[nl] = L;
+    s_end[nl] = ph[p].s_end;
+    nl += 1;
+    if (io_last && !match) { lay[nl] = io; s_end[nl] = ph[p].s_end; nl += 1; }
+    // stage tables of this phase
+    unsigned char regbit[4];
+    for (int k = 0; k < R; ++k) regbit[k] = bt.axbit[ph[p].T[k]];
+    for (int s = ph[p].s_begin; s < ph[p].s_end; ++s) {
+      int la = 0;
+      for (int k = 0; k < R; ++k) if (ph[p].T[k] == bt.st[s].axis) la = k;
+      out->lax[s] = (unsigned char)la;
+      out->st[s].qtab = parity_table(bt.st[s].mq, regbit, R, la);
+      out->st[s].vtab = parity_table(bt.st[s].mv, regbit, R, la);
+    }
+  }
+  out->nlayouts = nl;
+  out->F = F;
+  for (int p = 0; p < MAX_LAYOUTS + 2; ++p) out->s_end[p] = (unsigned char)((p < nl) ? s_end[p] : bt.nstages);
+  for (int p = 0; p < nl; ++p) {
+    for (int b = 0; b < (1 << R); ++b) {
+      uint64_t go = 0;
+      unsigned int so = 0;
+      for (int k = 0; k < R; ++k)
+        if ((b >> k) & 1) { go |= 1ull << lay[p].reg[k]; so |= 1u << canon(lay[p].reg[k]); }
+      out->gbits[p][b] = go;
+      out->sbits[p][b] = (unsigned short)sw(so);
+    }
+    for (int k = 0; k < MAX_THREAD_BITS; ++k) {
+      out->gtid[p][k] = (k < NTB) ? (1ull << lay[p].thr[k]) : 0ull;
+      out->stid[p][k] = (k < NTB) ? (unsigned short)sw(1u << canon(lay[p].thr[k])) : (unsigned short)0;
+    }
   }
   return nph;
 }
@@ -500,7 +590,8 @@ int flush_batch(gxsv_t* h) {
     if (TW == 0) TW = (bt.naxes >= R + 2) ? 4 : 1;
     if (R == 3) TW = 1;
     const int ltw = (TW == 8) ? 3 : (TW == 4) ? 2 : 0;
-    tb.nphases = plan_phases(bt, &tb, R, 5 + R + ltw);
+    const int nphases = plan_phases(bt, &tb, R, h->live_mask, 5 + R + ltw, h->tile_io);
+    if (nphases > MAX_PHASES) return fail(h, GXSV_EVALUE, "internal: batch needs %d phases", nphases);
     for (int k = 0; k < bt.nstages; ++k) {      // dispatch codes and packed operands of the stages (stage_by_variant)
       const Stage& st = tb.st[k];
       unsigned int variant;
@@ -511,8 +602,6 @@ int flush_batch(gxsv_t* h) {
       tb.hot[k].qtab = st.qtab;
       tb.hot[k].mq = st.mq;
     }
-    tb.prefetch = h->tile_prefetch;
-    if (tb.nphases > MAX_PHASES) return fail(h, GXSV_EVALUE, "internal: batch needs %d phases", tb.nphases);
     const uint64_t ntiles = 1ull << (n - (8 + R));            // CTA iterations: 8 warp tiles of 2^(5+R) amplitudes
     const size_t dyn = sizeof(double2) << (8 + R);
     if (!h->attr_tile) {     // per handle: function attributes belong to the device context
@@ -528,13 +617,10 @@ int flush_batch(gxsv_t* h) {
     uint64_t tgrid = std::min<uint64_t>(ntiles, (uint64_t)h->sm_count * (R == 3 ? 4 : 2));   // persistent: resident CTAs only
     int gl = h->chunk_log2;
     while (gl > 0 && (ntiles >> gl) < tgrid * 8) --gl;
-    static const bool log_shapes = std::getenv("GXSV_BATCH_LOG") != nullptr;
-    if (log_shapes) {
-      int nuni = 0;
-      for (int k = 0; k < bt.nstages; ++k) nuni += (tb.st[k].qtab == 0ull && tb.st[k].kind == 0 && !tb.st[k].acc) ? 1 : 0;
-      fprintf(stderr, "gxsv-pass n=%d axes=%d stages=%d phases=%d uniform=%d bits=", n, bt.naxes, bt.nstages, tb.nphases, nuni);
-      for (int a = 0; a < bt.naxes; ++a) fprintf(stderr, "%d%s", (int)bt.axbit[a], a + 1 < bt.naxes ? "," : "\n");
-    }
+    // GXSV_BATCH_LOG=1: one line per pass on stderr (shape, axis bits); =2: also the pass time (synchronises every pass)
+    static const int log_shapes = std::getenv("GXSV_BATCH_LOG") ? std::atoi(std::getenv("GXSV_BATCH_LOG")) : 0;
+    cudaEvent_t le0 = nullptr, le1 = nullptr;
+    if (log_shapes >= 2) { cudaEventCreate(&le0); cudaEventCreate(&le1); cudaEventRecord(le0, h->stream); }
     Launch L(h, GXSV_K_FUSED, 2.0 * 16.0 * std::ldexp(1.0, n), /*frame_aware=*/true);   // a pending frame was issued AFTER these stages
 #define GXSV_TILE_LAUNCH(RR, WW, SS) \
   k_fused_tile<RR, WW, SS><<<(int)tgrid, TPB, dyn, h->stream>>>(h->psi, hs, tb, ntiles, gl, h->partials, h->ctrl, slot, seq, fm)
@@ -546,6 +632,21 @@ int flush_batch(gxsv_t* h) {
     else if (sp) GXSV_TILE_LAUNCH(4, 1, true);
     else GXSV_TILE_LAUNCH(4, 1, false);
 #undef GXSV_TILE_LAUNCH
+    if (log_shapes) {
+      float ms = 0.f;
+      if (log_shapes >= 2) {
+        cudaEventRecord(le1, h->stream);
+        cudaEventSynchronize(le1);
+        cudaEventElapsedTime(&ms, le0, le1);
+        cudaEventDestroy(le0);
+        cudaEventDestroy(le1);
+      }
+      int nuni = 0;
+      for (int k = 0; k < bt.nstages; ++k) nuni += ((tb.code[k] & 7u) == SV_UNIQ) ? 1 : 0;
+      fprintf(stderr, "gxsv-pass n=%d axes=%d stages=%d phases=%d layouts=%d uniform=%d tw=%d ms=%.4f bits=", n, bt.naxes,
+              bt.nstages, nphases, tb.nlayouts, nuni, TW, ms);
+      for (int a = 0; a < bt.naxes; ++a) fprintf(stderr, "%d%s", (int)bt.axbit[a], a + 1 < bt.naxes ? "," : "\n");
+    }
   }
   Deferred d;
   d.first = seq;
@@ -951,7 +1052,7 @@ int gxsv_create(int max_qubits, int device, void* stream, gxsv_t** out) {
   if (const char* lf = std::getenv("GXSV_LAZY_FRAME")) h->lazy_frame = std::atoi(lf) != 0;
   if (const char* sp = std::getenv("GXSV_STAGE_PREFETCH")) h->stage_prefetch = std::atoi(sp) != 0;
   if (const char* tw = std::getenv("GXSV_TILE_WARPS")) { const int v = std::atoi(tw); if (v == 0 || v == 1 || v == 4 || v == 8) h->tile_warps = v; }
-  if (const char* tp = std::getenv("GXSV_TILE_PREFETCH")) h->tile_prefetch = std::atoi(tp) != 0;
+  if (const char* tp = std::getenv("GXSV_TILE_IO")) { const int v = std::atoi(tp); if (v >= 0 && v <= 2) h->tile_io = v; }
   if (const char* dv = std::getenv("GXSV_DEFER_VCZ")) h->defer_partner_cz = std::atoi(dv) != 0;
   if (const char* tr = std::getenv("GXSV_TILE_REGS")) h->tile_regs = (std::atoi(tr) == 3) ? 3 : 4;
   if (const char* an = std::getenv("GXSV_ANALYTIC_NORMS")) h->analytic_norms = std::atoi(an) ? 1 : 0;
@@ -1079,8 +1180,9 @@ int gxsv_set_option(gxsv_t* h, int key, int value) {
     case GXSV_OPT_DIST_QUEUE:
       h->dist_queue = value ? 1 : 0;
       return GXSV_OK;
-    case GXSV_OPT_TILE_PREFETCH:
-      h->tile_prefetch = value ? 1 : 0;
+    case GXSV_OPT_TILE_IO:
+      if (value < 0 || value > 2) return fail(h, GXSV_EVALUE, "tile I/O layout mode must be 0, 1 or 2");
+      h->tile_io = value;
       return GXSV_OK;
     case GXSV_OPT_TILE_WARPS:
       if (value != 0 && value != 1 && value != 4 && value != 8) return fail(h, GXSV_EVALUE, "warps per tile must be 0 (auto), 1, 4 or 8");
@@ -1110,7 +1212,7 @@ int gxsv_get_option(gxsv_t* h, int key, int* value) {
     case GXSV_OPT_TMA: *value = h->use_tma; return GXSV_OK;
     case GXSV_OPT_TILE_REGS: *value = h->tile_regs; return GXSV_OK;
     case GXSV_OPT_DIST_QUEUE: *value = h->dist_queue; return GXSV_OK;
-    case GXSV_OPT_TILE_PREFETCH: *value = h->tile_prefetch; return GXSV_OK;
+    case GXSV_OPT_TILE_IO: *value = h->tile_io; return GXSV_OK;
     case GXSV_OPT_TILE_WARPS: *value = h->tile_warps; return GXSV_OK;
     case GXSV_OPT_DEFER_VCZ: *value = h->defer_partner_cz ? 1 : 0; return GXSV_OK;
     default: return fail(h, GXSV_EVALUE, "unknown option %d", key);
@@ -2088,6 +2190,33 @@ int gxsv_ipc_close(gxsv_t* h) {
   for (int i = 0; i < 8; ++i)
     if (h->peer_psi[i]) { cudaIpcCloseMemHandle(h->peer_psi[i]); h->peer_psi[i] = nullptr; }
   return GXSV_OK;
+}
+
+int gxsv_plan_tile_layouts(int naxes, const unsigned char* axis_bits, int nstages, const unsigned char* stage_axis,
+                           unsigned long long live_mask, int reg_bits, int tile_log2, int io_mode, int* nlayouts,
+                           unsigned char* s_end, unsigned char* lax, unsigned long long* gbits, unsigned long long* gtid,
+                           unsigned short* sbits, unsigned short* stid) {
+  if (naxes < 1 || naxes > MAX_TILE_AXES || nstages < 1 || nstages > MAX_STAGES || (reg_bits != 3 && reg_bits != 4) ||
+      naxes < reg_bits || tile_log2 - reg_bits > MAX_THREAD_BITS || tile_log2 < naxes)
+    return -1;
+  static thread_local Batch bt;
+  static thread_local TileBatch tb;
+  memset(&bt, 0, sizeof bt);
+  memset(&tb, 0, sizeof tb);
+  bt.naxes = naxes;
+  bt.nstages = nstages;
+  for (int a = 0; a < naxes; ++a) bt.axbit[a] = axis_bits[a];
+  for (int k = 0; k < nstages; ++k) { if (stage_axis[k] >= naxes) return -1; bt.st[k].axis = stage_axis[k]; }
+  const int nph = plan_phases(bt, &tb, reg_bits, live_mask, tile_log2, io_mode);
+  if (nph > MAX_PHASES) return nph;
+  *nlayouts = tb.nlayouts;
+  for (int p = 0; p < MAX_LAYOUTS; ++p) {
+    s_end[p] = tb.s_end[p];
+    for (int b = 0; b < 16; ++b) { gbits[p * 16 + b] = tb.gbits[p][b]; sbits[p * 16 + b] = tb.sbits[p][b]; }
+    for (int k = 0; k < MAX_THREAD_BITS; ++k) { gtid[p * MAX_THREAD_BITS + k] = tb.gtid[p][k]; stid[p * MAX_THREAD_BITS + k] = tb.stid[p][k]; }
+  }
+  for (int k = 0; k < nstages; ++k) lax[k] = tb.lax[k];
+  return nph;
 }
 
 int gxsv_flush_batch(gxsv_t* h) {

@@ -70,7 +70,6 @@ __device__ __forceinline__ double cnorm2(const double2 a) { return fma(a.x, a.x,
 // streaming accesses: the state is touched once per pass and is far larger than L2
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ double2 ld_amp(const double2* p) { return __ldcs(p); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p))); }
 __device__ __forceinline__ void st_amp(double2* p, const double2 v) { __stcs(p, v); }
 
 // ---------------------------------------------------------------------------
@@ -511,31 +510,6 @@ __device__ __forceinline__ void stage_on_axis(double2 (&v)[1 << NB], const Stage
   else stage_pairs<NB, AX, 2, true, true>(v, st, st.a, tq, tv, nrm0, nrm1);
 }
 
-// The same dispatch driven by ONE host-made code per stage (tile kernel): register axis, variant and the accumulate
-// flag in one byte (TileBatch::code), and
-// the three operands every common variant needs (multiplier, sign table, sign mask) come from a packed table that the
-// caller fetches one stage ahead.  Without it a stage began with a chain of five dependent constant loads (register
-// axis -> kind -> flags -> table -> multiplier), each an indexed LDC round trip with only four warps per scheduler
-// to hide it (ncu, config 3: short-scoreboard stalls 1.9 - 3.3 per issued instruction).
-enum : unsigned int { SV_UNIQ = 0, SV_FAST = 1, SV_FAST_ACC = 2, SV_K0_SIGNED = 3, SV_K1 = 4, SV_GENERAL = 5 };
-struct StageHot {
-  double2 a;                    // Stage::a
-  unsigned long long qtab, mq;  // Stage::qtab, Stage::mq
-};
-template <int NB, int AX>
-__device__ __forceinline__ void stage_by_variant(double2 (&v)[1 << NB], const unsigned int variant, const Stage& st,
-                                                 const double2 a, const unsigned long long tq, const uint64_t gfixed,
-                                                 double& nrm0, double& nrm1) {
-  if (variant == SV_UNIQ) return stage_pairs<NB, AX, 0, false, false, true>(v, st, a, tq, 0ull, nrm0, nrm1);
-  if (variant == SV_FAST) return stage_pairs<NB, AX, 0, false, false>(v, st, a, tq, 0ull, nrm0, nrm1);
-  if (variant == SV_FAST_ACC) return stage_pairs<NB, AX, 0, true, false>(v, st, a, tq, 0ull, nrm0, nrm1);
-  const unsigned int gpar_v = __popcll(gfixed & st.mv);
-  const unsigned long long tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x8080808080808080ull : 0ull);
-  if (variant == SV_K0_SIGNED) stage_pairs<NB, AX, 0, true, true>(v, st, a, tq, tv, nrm0, nrm1);
-  else if (variant == SV_K1) stage_pairs<NB, AX, 1, true, true>(v, st, a, tq, tv, nrm0, nrm1);
-  else stage_pairs<NB, AX, 2, true, true>(v, st, a, tq, tv, nrm0, nrm1);
-}
-
 // Batch on at most three physical bits: a thread owns the 2^A amplitudes of one group in registers and applies the
 // stages in order (64 registers, 4 CTAs per SM; the per-thread stage accumulators live in shared memory).
 // CTAs take chunks of 2^glog consecutive 256-group blocks (glog = 0: plain grid stride).
@@ -591,51 +565,78 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_batch(double2* __restrict__ ps
 }
 
 // ---------------------------------------------------------------------------
-// Batched lazy projections on MORE than three physical bits (4 <= A <= 6): the register file holds 2^3 amplitudes per
-// thread at 4 CTAs per SM (k_fused_batch above), so a batch whose stages touch up to 6 distinct bits is executed in
-// PHASES.  Every WARP owns a tile of 2^8 amplitudes = 2^A axis combinations x 2^(8-A) consecutive dense indices; the 8
-// warps of a CTA take 8 consecutive warp tiles, so that the CTA as a whole still reads 2^(11-A) consecutive amplitudes
-// (>= 512 B) per axis combination.  In a phase every thread keeps the 2^3 combinations of three of the axes in
-// registers (the other A - 3 axis values and the dense index are fixed per lane) and applies the consecutive stages
-// that act on those three axes; between phases the warp transposes its tile through its private 4 KB of shared
-// memory to the register assignment of the next phase.  Only __syncwarp is needed: the warps stay independent, so the
-// FP64 work of one warp overlaps the loads and stores of the others exactly as in the single-phase kernel.
-// (Measured first: the same scheme with ONE tile of 2^11 amplitudes per CTA and __syncthreads between phases ran 8 stages
-// on 5 axes in 1.37 ms at 27 qubits against 0.81 ms for 8 stages on 3 axes in k_fused_batch: the CTA-wide barriers
-// serialise the memory and FP64 phases.)  HBM traffic stays one read and one write of the register per pass whatever
-// the number of stages and phases; the host plans the phases greedily (longest run of stages on <= 3 distinct axes; at
-// most MAX_PHASES per pass).  Tiles are handed to CTAs in chunks of 2^glog consecutive CTA tiles.
+// Batched lazy projections on MORE than three physical bits (4 <= A <= 7): the register file cannot hold 2^A amplitudes
+// per thread, so a batch whose stages touch up to 7 distinct bits is executed in PHASES on TILES.
+//   tile   = 2^WT amplitudes owned by a GROUP of TW warps (TW = 1: WT = 5 + R, a private warp tile; TW = 4: WT = 7 + R,
+//            two groups per CTA): the 2^A combinations of the batch axes x the 2^F combinations of the F = WT - A lowest
+//            live physical bits that are not axes.  The tile-index bits are thus WT physical bit positions.
+//   layout = which R of those bits a thread keeps in registers (2^R amplitudes) and which thread-id bit stands for each
+//            of the others.  Everything is tabulated by the host per layout (TileBatch::gbits / gtid for global
+//            offsets, sbits / stid for slots of the group's shared-memory tile): the kernel ORs / XORs table entries.
+//   phase  = a layout + the consecutive stages whose axes are register bits in it.  Between two layouts the group
+//            transposes through its shared tile (only the group synchronises: __syncwarp, or a named barrier over
+//            32 TW threads — groups and CTAs stay independent, so the FP64 work of one overlaps the loads of others).
+//   I/O    = the first layout is the one the tile is LOADED in, the last one the one it is STORED in.  When three or
+//            more batch axes sit on the lowest physical bits (QFT patterns: 4 - 6 of the axes of a pass on bits 0 - 5)
+//            the lanes of a direct layout would be >= 128 bytes apart; the host then puts an extra stage-less layout in
+//            front and at the end whose thread bits are the LOWEST bits of the tile — axes or not — so that every
+//            warp-wide access is one contiguous 512-byte run; otherwise the lanes run over the dense bits of the first /
+//            last phase directly (two more transposes cost 8 % on config 2).  Measured before this (config 4, 32 live
+//            qubits): such passes at 0.42 - 0.61 of the copy rate against 0.90 for passes on high bits.
+// HBM traffic is one read and one write of the register per pass whatever the number of stages and layouts.
+// Measured on the way (profiles/r02_summary.md): one 2^11 tile per CTA with __syncthreads between phases (1.37 ms for 8
+// stages on 5 axes at 27 qubits), private warp tiles only (runs of 64 bytes on 7 axes: 0.58 of the copy rate on
+// config 3 against 0.80 with four warps per tile), tiles shared by all 8 warps (9 % slower than 4), an L2 prefetch of
+// the next tile (prefetch.global.L2: within +-2 %), streaming (ld.global.cs) loads (1 - 2 % slower than L1-allocating).
 // ---------------------------------------------------------------------------
-constexpr int TILE_LOG2 = 11;      // amplitudes per CTA iteration
-constexpr int WTILE_LOG2 = 8;      // amplitudes per warp tile
+constexpr int TILE_LOG2 = 11;      // amplitudes per CTA iteration of k_fused_tma
 constexpr int MAX_TILE_AXES = 7;
-constexpr int MAX_PHASES = 4;
+constexpr int MAX_PHASES = 4;      // phases with stages
+constexpr int MAX_LAYOUTS = MAX_PHASES + 2;
+constexpr int MAX_THREAD_BITS = 8; // log2 TPB
+enum : unsigned int { SV_UNIQ = 0, SV_FAST = 1, SV_FAST_ACC = 2, SV_K0_SIGNED = 3, SV_K1 = 4, SV_GENERAL = 5 };
+struct StageHot {
+  double2 a;                    // Stage::a
+  unsigned long long qtab, mq;  // Stage::qtab, Stage::mq
+};
 struct TileBatch {
-  int nstages, naxes, nphases;
-  int prefetch;                               // != 0: ask the next warp tile into L2 while the current one is computed
+  int nstages, naxes, nlayouts, F;
   unsigned char lax[MAX_STAGES];              // register slot (0..R-1) of the axis of every stage inside its phase
-  unsigned char s_begin[MAX_PHASES], s_end[MAX_PHASES];
+  unsigned char s_end[MAX_LAYOUTS + 2];       // stages [s_end[p-1], s_end[p]) run in layout p
   unsigned char code[MAX_STAGES + 4];         // 32 * lax + 16 * (accumulate the norm) + variant (SV_*), see stage_by_variant
   StageHot hot[MAX_STAGES + 1];               // the operands of the common variants, packed (one spare entry: fetched ahead)
-  // everything a thread needs to address its 2^R amplitudes is tabulated by the host (no per-tile index arithmetic):
-  unsigned long long gbits[MAX_PHASES][16];   // physical offset of register slot b in phase p
-  unsigned long long goth[MAX_PHASES][4];     // physical offset of the i-th axis fixed per lane (taken iff bit i of r = lane >> F)
-  unsigned short sbits[MAX_PHASES][16];       // the same two as offsets inside the warp's shared-memory tile (<< F applied)
-  unsigned short soth[MAX_PHASES][4];
+  unsigned long long gbits[MAX_LAYOUTS][16];             // physical offset of register slot b in layout p
+  unsigned long long gtid[MAX_LAYOUTS][MAX_THREAD_BITS]; // physical offset contributed by bit i of the thread's index in its group
+  unsigned short sbits[MAX_LAYOUTS][16];                 // the same two as (swizzled) slot offsets inside the group's shared tile
+  unsigned short stid[MAX_LAYOUTS][MAX_THREAD_BITS];
   double nscale[MAX_STAGES];
   Stage st[MAX_STAGES];
 };
-// R = register axes per phase: 3 (2^3 amplitudes per thread, 64 registers, 4 CTAs per SM) or 4 (2^4 amplitudes per
-// thread, 128 registers, 2 CTAs per SM: fewer phases, runs twice as long).
-// TW = warps that share one tile (1, 4 or 8): a tile is 2^A axis combinations x 2^F consecutive amplitudes with
-// F = 5 + R + log2(TW) - A, so a pass on 7 axes reads runs of 64 bytes with private warp tiles (TW = 1) — measured
-// at 27 qubits: 0.58 of the copy rate against 0.87 for the 256-byte runs of a 5-axis pass, and 1.8 ms against 1.1 ms
-// when the seven axes are the top bits instead of spread — but runs of 256 / 512 bytes when four / eight warps share
-// the tile.  The group then transposes through its shared tile behind a named barrier (bar.sync on 32 TW threads)
-// instead of __syncwarp; groups of one CTA and the CTAs of an SM stay independent of each other.
-// SP = the stage operands are staged in shared memory and fetched one stage ahead by asm-volatile loads (which neither
-// the compiler nor ptxas sinks to the first use); SP = false reads them from the kernel parameters, where the fetch of
-// stage s + 1 ends up at the bottom of stage s whatever the source order.
+
+// One host-made code per stage (TileBatch::code: register axis, variant and the accumulate flag in one byte) and the
+// three operands every common variant needs (multiplier, sign table, sign mask) in a packed table that the kernel
+// fetches one stage ahead.  Without it a stage began with a chain of five dependent constant loads (register axis ->
+// kind -> flags -> table -> multiplier), each an indexed LDC round trip with only four warps per scheduler to hide it
+// (ncu, config 3: short-scoreboard stalls 1.9 - 3.3 per issued instruction).
+template <int NB, int AX>
+__device__ __forceinline__ void stage_by_variant(double2 (&v)[1 << NB], const unsigned int variant, const Stage& st,
+                                                 const double2 a, const unsigned long long tq, const uint64_t gfixed,
+                                                 double& nrm0, double& nrm1) {
+  if (variant == SV_UNIQ) return stage_pairs<NB, AX, 0, false, false, true>(v, st, a, tq, 0ull, nrm0, nrm1);
+  if (variant == SV_FAST) return stage_pairs<NB, AX, 0, false, false>(v, st, a, tq, 0ull, nrm0, nrm1);
+  if (variant == SV_FAST_ACC) return stage_pairs<NB, AX, 0, true, false>(v, st, a, tq, 0ull, nrm0, nrm1);
+  const unsigned int gpar_v = __popcll(gfixed & st.mv);
+  const unsigned long long tv = st.vtab ^ (((gpar_v ^ st.neg) & 1u) ? 0x8080808080808080ull : 0ull);
+  if (variant == SV_K0_SIGNED) stage_pairs<NB, AX, 0, true, true>(v, st, a, tq, tv, nrm0, nrm1);
+  else if (variant == SV_K1) stage_pairs<NB, AX, 1, true, true>(v, st, a, tq, tv, nrm0, nrm1);
+  else stage_pairs<NB, AX, 2, true, true>(v, st, a, tq, tv, nrm0, nrm1);
+}
+
+// R = register bits per layout: 3 (2^3 amplitudes per thread, 64 registers, 4 CTAs per SM) or 4 (2^4 amplitudes per
+// thread, 128 registers, 2 CTAs per SM: fewer phases).  TW = warps per group (1, 4 or 8).  SP = the stage operands are
+// staged in shared memory and fetched one stage ahead by asm-volatile loads (which neither the compiler nor ptxas sinks
+// to the first use); SP = false reads them from the kernel parameters, where the fetch of stage s + 1 ends up at the
+// bottom of stage s whatever the source order.
 template <int R, int TW, bool SP>
 __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* __restrict__ psi, const __grid_constant__ Holes hs,
                                                       const __grid_constant__ TileBatch bt, const uint64_t ntiles,
@@ -643,13 +644,16 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
                                                       Res* res, const unsigned long long seq, const int fin_mode) {
   constexpr int LTW = (TW == 1) ? 0 : (TW == 2) ? 1 : (TW == 4) ? 2 : 3;
   constexpr int WT = 5 + R + LTW;                   // log2 amplitudes per group tile
+  constexpr int NTB = 5 + LTW;                      // thread-index bits of a group
   constexpr int GT = 32 * TW;                       // threads per group
   constexpr int NG = TPB / GT;                      // groups per CTA
   static_assert(NG == 1 || NG == 2 || TW == 1, "named barriers are written out for two groups");
   constexpr int D = 1 << R;
   extern __shared__ double2 tile_all[];             // NG groups x 2^WT amplitudes (dynamic) = 2^(8+R) amplitudes per CTA
   __shared__ double sacc[MAX_STAGES][TPB];
-  const int F = WT - bt.naxes;
+  __shared__ __align__(16) StageHot shot[MAX_STAGES + 1];
+  __shared__ unsigned int scode[MAX_STAGES + 4];
+  const int F = bt.F;
   const int tid = threadIdx.x, tg = tid & (GT - 1), grp = tid / GT;
   double2* tile = tile_all + ((size_t)grp << WT);
   auto group_sync = [&]() {
@@ -658,17 +662,10 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
     else if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory");   // immediate ids: a register id makes
     else asm volatile("bar.sync 2, %0;" ::"n"(GT) : "memory");                  // ptxas reserve all 16 barriers
   };
-  const unsigned int f = tg & ((1u << F) - 1u);
-  // shared-memory slots are XOR-swizzled: bit 2 of the slot index ^= parity of the bits above it, so that the 8 lanes of
-  // a quarter warp (one 128-byte wavefront of 16-byte accesses) always hit 8 different bank groups — without it passes on
-  // 7 axes (F = 2) ran with 2-way conflicts on every transpose (ncu: 53 % of the shared wavefronts).  The swizzle is
-  // linear over XOR and the parts of an index occupy disjoint bits, so the host tabulates it per part.
-  const unsigned int fsw = f ^ ((__popc(f >> 3) & 1u) << 2);
-  const int r = tg >> F;
   const double g = ctrl->g;
-  const int nphases = bt.nphases;
-  __shared__ __align__(16) StageHot shot[MAX_STAGES + 1];
-  __shared__ unsigned int scode[MAX_STAGES + 4];
+  const int nlayouts = bt.nlayouts;
+#pragma unroll
+  for (int k = 0; k < MAX_STAGES; ++k) sacc[k][tid] = 0.0;
   if (SP) {
     if (tid <= MAX_STAGES) { shot[tid] = bt.hot[tid]; scode[tid] = bt.code[tid]; }
     __syncthreads();
@@ -687,54 +684,35 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
       m = bt.hot[k].mq;
     }
   };
-  const bool pf = bt.prefetch != 0;
-  const unsigned int pfmask = (F >= 3) ? 7u : ((1u << F) - 1u);   // lanes that start a 128-byte line (or a shorter run)
+  // this thread's part of the addresses in layout p: uniform table entries selected by the bits of its index in the group
+  // (a table indexed by the thread itself — a per-thread index into the kernel parameters — faulted on sm_100a with
+  // CUDA 12.9 although the emulated addresses were all in range; the uniform form costs a few predicated ORs)
+  auto thread_off = [&](int p, uint64_t& go, unsigned int& so) {
+    go = 0;
+    so = 0;
 #pragma unroll
-  for (int k = 0; k < MAX_STAGES; ++k) sacc[k][tid] = 0.0;
+    for (int i = 0; i < NTB; ++i)
+      if ((tg >> i) & 1) { go |= bt.gtid[p][i]; so ^= bt.stid[p][i]; }
+  };
   // the i-th CTA tile of this CTA: chunks of 2^glog consecutive tiles, chunks dealt round robin (monotonic in i)
   const uint64_t gmask = (1ull << glog) - 1ull;
   auto tile_of = [&](uint64_t i) { return (((uint64_t)blockIdx.x + (i >> glog) * gridDim.x) << glog) + (i & gmask); };
-  auto base_of = [&](uint64_t t) { return expand(((t * NG + grp) << F) | f, hs); };
-  uint64_t i = 0, t = tile_of(0);
-  uint64_t base_next = (t < ntiles) ? base_of(t) : 0ull;
-  while (t < ntiles) {
-    const uint64_t base = base_next;
+  uint64_t gfirst;
+  unsigned int sfirst;
+  thread_off(0, gfirst, sfirst);                    // the load layout does not depend on the tile
+  uint64_t i = 0;
+  for (uint64_t t = tile_of(0); t < ntiles; t = tile_of(++i)) {
+    // physical index of the group's tile (all tile-index bits 0): the same for every thread of the group
+    const uint64_t base = expand((t * NG + grp) << F, hs);
     double2 v[D];
-    // offsets of the axis values fixed per lane: uniform table entries selected by the bits of r (a table indexed by
-    // r itself — a per-thread index into the kernel parameters — faulted on sm_100a with CUDA 12.9 although the
-    // emulated addresses were all in range; the uniform form costs three predicated ORs)
-    auto lane_off = [&](int p, uint64_t bs, uint64_t& go, unsigned int& so) {
-      go = bs;
-      so = fsw;
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if ((r >> k) & 1) { go |= bt.goth[p][k]; so ^= bt.soth[p][k]; }
-    };
-    uint64_t gthread;
-    unsigned int sthread;
-    lane_off(0, base, gthread, sthread);
+    uint64_t gthread = base | gfirst;               // physical index of this thread's amplitudes with the register bits 0
+    unsigned int sthread = sfirst;                  // its slot in the group's shared tile, register bits 0
     {
-      double2* src = psi + gthread;
+      const double2* src = psi + gthread;
 #pragma unroll
       for (int b = 0; b < D; ++b) {
-        const double2 a = ld_amp(src + bt.gbits[0][b]);
-        v[b] = make_double2(g * a.x, g * a.y);    // the pending normalisation, once per pass
-      }
-    }
-    // The warp's NEXT tile is asked into L2 now: a warp computes on its tile for thousands of cycles with its 2^R loads
-    // long retired, so without this only the warps that happen to sit in their load phase keep HBM busy (ncu, config 2:
-    // long-scoreboard stalls = a quarter of the warp time).  One request per 128-byte line; the index expansion is
-    // the one the next iteration needs anyway.
-    const uint64_t tn = tile_of(++i);
-    if (tn < ntiles) {
-      base_next = base_of(tn);
-      if (pf && (f & pfmask) == 0u) {
-        uint64_t gn;
-        unsigned int sn;
-        lane_off(0, base_next, gn, sn);
-        const double2* nsrc = psi + gn;
-#pragma unroll
-        for (int b = 0; b < D; ++b) prefetch_l2(nsrc + bt.gbits[0][b]);
+        const double2 a = src[bt.gbits[0][b]];      // L1-allocating: measured 1 - 2 % faster than ld.global.cs here
+        v[b] = make_double2(g * a.x, g * a.y);      // the pending normalisation, once per pass
       }
     }
     // stage operands are fetched one stage ahead (s counts from 0 through the phases: uniform, so are the loads)
@@ -743,8 +721,7 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
     double2 a;
     unsigned long long qtab, mq;
     fetch(0, code, a, qtab, mq);
-    for (int p = 0; p < nphases; ++p) {
-      // gthread = physical index of this thread's group (register axes = 0), sthread = its slot base in the warp tile
+    for (int p = 0; p < nlayouts; ++p) {
       const int s_end = bt.s_end[p];
       for (; s < s_end; ++s) {
         unsigned int code_n;
@@ -765,10 +742,12 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
         qtab = qtab_n;
         mq = mq_n;
       }
-      if (p + 1 < nphases) {
-        // transpose through the warp's private tile to the register assignment of the next phase
+      if (p + 1 < nlayouts) {
+        // transpose through the group's tile to the next layout
         const unsigned int s_old = sthread;
-        lane_off(p + 1, base, gthread, sthread);
+        uint64_t gn;
+        thread_off(p + 1, gn, sthread);
+        gthread = base | gn;
         const unsigned int s_new = sthread;
         group_sync();                             // every thread has read its slots of the previous transpose
 #pragma unroll
@@ -782,7 +761,6 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
         for (int b = 0; b < D; ++b) st_amp(dst + bt.gbits[p][b], v[b]);
       }
     }
-    t = tn;
   }
   double acc[MAX_STAGES];
 #pragma unroll

@@ -65,8 +65,10 @@ enum {
   GXSV_OPT_DIST_QUEUE = 10,/* sharded STRICT mode: 1 = projections whose outcome probability is analytic are queued like in
                             * the single-GPU strict mode (gxsv_project_qubit then returns NaN norms and the caller collects
                             * them later with gxsv_take_norms); everything else still returns its local half-norms at once */
-  GXSV_OPT_TILE_PREFETCH = 11, /* tuning: 1 = the multi-axis batched pass asks every warp's next tile into L2
-                            * (prefetch.global.L2) while the current one is computed; 0 (default): measured faster */
+  GXSV_OPT_TILE_IO = 11,   /* tuning: load / store layouts of the multi-axis batched pass: 1 (default) = when three or more batch axes
+                            * lie below physical bit 6 the tile is loaded and stored with the lanes on its LOWEST bits (contiguous
+                            * 512-byte runs) and transposed to / from the first / last phase in shared memory; 0 = never
+                            * (lanes on the dense bits of the first / last phase), 2 = always */
   GXSV_OPT_TILE_WARPS = 13,/* tuning: warps that share one tile of the multi-axis batched pass: 0 (default) = by the number
                             * of axes (4 from 6 axes on: runs of >= 256 bytes), 1 = private warp tiles, 4, 8 */
   GXSV_OPT_DEFER_VCZ = 12  /* tuning: 1 (default) = a queued projection leaves the CZs of the newly materialised partner
@@ -212,6 +214,18 @@ int gxsv_ipc_export(gxsv_t* h, unsigned char handle_out[64]);
 int gxsv_ipc_open(gxsv_t* h, int slot, const unsigned char handle[64]);
 int gxsv_ipc_close(gxsv_t* h);
 int gxsv_swap_peer(gxsv_t* h, int q, int slot, int my_bit, double fre, double fim);
+/* Host-side planner of the multi-axis batched pass (k_fused_tile), exposed so that its tables can be checked without a
+ * device: for a batch of `nstages` fused projections whose k-th stage acts on batch axis stage_axis[k] (physical bit
+ * axis_bits[stage_axis[k]]), returns the number of register phases and fills, per layout p < *nlayouts (at most 6):
+ * s_end[p] (stages run in layouts 0..p), gbits[16 p + b] / sbits[16 p + b] (physical offset / shared-tile slot of register
+ * slot b), gtid[8 p + i] / stid[8 p + i] (the same for bit i of a thread's index in its group), and lax[k] (register slot
+ * of stage k's axis).  live_mask = live physical bits, reg_bits = 3 | 4, tile_log2 = log2 amplitudes per tile, io_mode as
+ * GXSV_OPT_TILE_IO.  Returns -1 on invalid arguments; a result > 4 means the batch does not fit (tables not filled). */
+int gxsv_plan_tile_layouts(int naxes, const unsigned char* axis_bits, int nstages, const unsigned char* stage_axis,
+                           unsigned long long live_mask, int reg_bits, int tile_log2, int io_mode, int* nlayouts,
+                           unsigned char* s_end, unsigned char* lax, unsigned long long* gbits, unsigned long long* gtid,
+                           unsigned short* sbits, unsigned short* stid);
+
 /* launch the queued batched projections now (everything this shard still has to do to its register must be on the
  * stream BEFORE the barrier that precedes a peer swap: the partner reads this register right after that barrier) */
 int gxsv_flush_batch(gxsv_t* h);

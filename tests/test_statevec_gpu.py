@@ -474,28 +474,28 @@ def test_batched_passes_on_many_axes_against_oracle(n, axes, glog, tma):
         assert passes <= 16          # 48 stages: at least three per pass on average
 
 
-@pytest.mark.parametrize("defer,prefetch,tw", [(1, 0, 0), (0, 0, 4), (1, 1, 8), (1, 0, 1), (1, 0, 4)])
+@pytest.mark.parametrize("defer,io,tw", [(1, 1, 0), (0, 0, 4), (1, 2, 8), (1, 2, 1), (1, 2, 4), (1, 0, 1)])
 @pytest.mark.parametrize("axes,batch,glog", [(7, 12, 0), (7, 12, 2), (6, 12, 1), (4, 12, 0), (3, 12, 0)])
 @pytest.mark.parametrize("n", [14, 17, 20])
-def test_twelve_stage_passes_deferred_partner_cz_and_prefetch(n, axes, batch, glog, defer, prefetch, tw):
+def test_twelve_stage_passes_deferred_partner_cz_and_layouts(n, axes, batch, glog, defer, io, tw):
     """The bench-default pass shape (up to 12 stages on up to 7 axes, 2^4 amplitudes per thread) against the oracle, with
     the round-2 kernel variants switched both ways: partner CZs left queued (GXSV_OPT_DEFER_VCZ, the default) or applied
-    as signs inside the stage, next-tile L2 prefetch on / off, tiles private to a warp or shared by 4 / 8 warps (tw;
-    0 = chosen by the number of axes).  Mostly |+> partners and XY-plane measurements, as in
+    as signs inside the stage, extra load / store layouts never / when an axis is low / always (io), tiles private to a
+    warp or shared by 4 / 8 warps (tw; 0 = chosen by the number of axes).  Mostly |+> partners and XY-plane measurements, as in
     transpiled patterns (the 6-FMA butterfly with per-pair and thread-uniform signs), mixed with |-> / planar partners and
     arbitrary measurement axes (the general stages); CZs hang on both the measured and the new qubit, and some
     measured qubits are the partners of earlier stages of the same pass (their deferred CZs come back as that stage's
     own signs)."""
     from graphix_b200 import _lib
 
-    rng = np.random.default_rng(7000 * n + 100 * axes + 10 * glog + 2 * defer + prefetch + 1000000 * tw)
+    rng = np.random.default_rng(7000 * n + 100 * axes + 10 * glog + 2 * defer + io + 1000000 * tw)
     psi = rand_state(rng, n)
     dev = _sv(psi, n + 1, fusion=2, strict=False, batch=batch)
     dev.set_option(_lib.OPT_BATCH_AXES, axes)
     dev.set_option(_lib.OPT_CHUNK_LOG2, glog)
     dev.set_option(_lib.OPT_TILE_REGS, 4)
     dev.set_option(_lib.OPT_DEFER_VCZ, defer)
-    dev.set_option(_lib.OPT_TILE_PREFETCH, prefetch)
+    dev.set_option(_lib.OPT_TILE_IO, io)
     dev.set_option(_lib.OPT_TILE_WARPS, tw)
     orc = OracleStatevector(psi, max_qubits=n + 1)
     npass0 = dev.stats()["fused"]["launches"]

@@ -51,10 +51,10 @@ def main():
     rows = []
     hi = n - 1
 
-    def run(label, axes, stages, batch_axes, glog, tma=int(os.environ.get("MB_TMA", "0")), prefetch=0, tw=0):
+    def run(label, axes, stages, batch_axes, glog, tma=int(os.environ.get("MB_TMA", "0")), io=1, tw=0):
         sv.set_option(_lib.OPT_TMA, tma)
         sv.set_option(_lib.OPT_TILE_WARPS, tw)
-        sv.set_option(_lib.OPT_TILE_PREFETCH, prefetch)
+        sv.set_option(_lib.OPT_TILE_IO, io)
         sv.set_option(_lib.OPT_TILE_REGS, int(os.environ.get("MB_TILE_REGS", "4")))
         sv.set_option(_lib.OPT_BATCH_AXES, batch_axes)
         sv.set_option(_lib.OPT_CHUNK_LOG2, glog)
@@ -74,9 +74,9 @@ def main():
         st = sv.stats()["fused"]
         ms = st["device_ms"] / max(st["launches"], 1)
         gbs = st["algo_bytes"] / (st["device_ms"] * 1e-3) / 1e9 if st["device_ms"] else 0.0
-        rows.append({"n": n, "case": label, "prefetch": prefetch, "tile_warps": tw, "axes": list(axes), "stages": stages, "batch_axes": batch_axes, "glog": glog,
+        rows.append({"n": n, "case": label, "io": io, "tile_warps": tw, "axes": list(axes), "stages": stages, "batch_axes": batch_axes, "glog": glog,
                      "launches": st["launches"], "ms_per_pass": ms, "algo_GBps": gbs})
-        print(f"n={n} {label:28s} tw={tw} axes={str(list(axes)):26s} stages={stages} A<={batch_axes} glog={glog}: "
+        print(f"n={n} {label:34s} tw={tw} io={io} axes={str(list(axes)):26s} stages={stages} A<={batch_axes} glog={glog}: "
               f"{st['launches']:3d} passes {ms:9.4f} ms  {gbs:7.1f} GB/s", flush=True)
 
     lowmid = (9, 10, 11)
@@ -94,13 +94,25 @@ def main():
     seven_top = tuple(range(hi - 6, hi + 1))
     # 5) warps per tile (run length per axis combination): private warp tiles against tiles shared by 4 / 8 warps
     seven7 = dict(stages=7, batch_axes=7)
-    for tw in (1, 4, 8):
+    for tw in ((4,) if quick else (1, 4, 8)):
         run("7 axes spread, 7 stages", seven, 7, 7, 3, tw=tw)
         run("7 axes top, 7 stages", seven_top, 7, 7, 3, tw=tw)
         run("7 axes spread, 12 stages", seven, 12, 7, 3, tw=tw)
         run("6 axes, 8 stages", six, 8, 6, 3, tw=tw)
         run("5 axes spread, 8 stages", five_spread, 8, 5, 3, tw=tw)
         run("4 axes spread, 12 stages", (9, n // 2, hi - 2, hi), 12, 4, 3, tw=tw)
+    # 6) batch axes on the lowest physical bits (QFT patterns: 60 % of the passes): extra load / store layouts off / on
+    low7 = (0, 1, 12, n // 2, hi - 5, hi - 2, hi)
+    low7b = (1, 3, 12, n // 2, hi - 5, hi - 2, hi)
+    low4 = (0, n // 2, hi - 2, hi)
+    for io in (0, 1, 2):
+        run("7 axes incl. bits 0,1, 7 stages", low7, 7, 7, 3, io=io)
+        run("7 axes incl. bits 1,3, 7 stages", low7b, 7, 7, 3, io=io)
+        run("7 axes incl. bits 0,1, 12 stages", low7, 12, 7, 3, io=io)
+        run("4 axes incl. bit 0, 12 stages", low4, 12, 4, 3, io=io)
+        run("7 axes spread, 7 stages", seven, 7, 7, 3, io=io)
+        run("7 axes top, 7 stages", seven_top, 7, 7, 3, io=io)
+        run("5 axes spread, 8 stages", five_spread, 8, 5, 3, io=io)
     print("norm2", sv.norm2())
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/microbench_batch_{n}.json", "w") as f:
