@@ -104,8 +104,8 @@ struct gxsv {
                            // stages per pass, see kernels.cuh) when the layout allows
   int stage_prefetch = 1;         // k_fused_tile fetches the operands of stage s + 1 from shared memory while stage s runs (GXSV_STAGE_PREFETCH)
   int tile_warps = 0;             // warps sharing one tile of k_fused_tile: 0 = by the number of axes, else 1 / 4 / 8 (GXSV_TILE_WARPS)
-  int tile_io = 1;                // k_fused_tile: extra load / store layouts over the lowest tile bits: 0 never, 1 when three or more
-                                  // batch axes lie below bit 6 (default), 2 always (GXSV_TILE_IO)
+  int tile_io = 1;                // k_fused_tile: extra load / store layouts over the lowest tile bits: 0 never, 1 when the three
+                                  // lowest tile bits are all batch axes (default), 2 always (GXSV_TILE_IO)
   bool defer_partner_cz = true;   // batched stages leave the partner's CZs queued (GXSV_DEFER_VCZ=0: apply them in the stage)
   int batch_max = 0;       // > 0: queue up to this many fused projections and run them in one pass (non-strict only)
   Batch batch;             // the open batch (nstages == 0: none)
@@ -296,8 +296,8 @@ unsigned long long parity_table(uint64_t mask, const unsigned char* regbit, int 
 // keeps R of them in registers and gives each of the others a bit of the thread's index in its group.
 //   * a phase keeps its (padded) axes in registers; its thread bits are ordered so that the three lowest lane bits land
 //     in different bank groups of the (XOR-folded) shared tile whenever possible;
-//   * the first / last layout is what the tile is loaded / stored in.  io_mode 1: when three or more batch axes lie
-//     below bit 6, an extra stage-less layout is put in front / at the end whose thread bits are the LOWEST tile-index
+//   * the first / last layout is what the tile is loaded / stored in.  io_mode 1: when the three lowest tile bits are
+//     all batch axes, an extra stage-less layout is put in front / at the end whose thread bits are the LOWEST tile-index
 //     bits in physical order and whose register bits are the R highest — unless the first / last phase happens to
 //     have exactly those register bits; io_mode 0: never, 2: always.
 int plan_phases(const Batch& bt, TileBatch* out, int R, uint64_t live_mask = 0, int tile_log2 = 0, int io_mode = 1) {
@@ -362,12 +362,17 @@ int plan_phases(const Batch& bt, TileBatch* out, int R, uint64_t live_mask = 0, 
   Layout io;
   for (int k = 0; k < NTB; ++k) io.thr[k] = pos[k];
   for (int k = 0; k < R; ++k) io.reg[k] = pos[NTB + k];
-  // Direct lanes run over the lowest NON-axis bits: with up to two axes below them a warp access still falls into a few
-  // 128-byte lines (measured at 27 qubits: no loss), with three or more the lanes are >= 128 bytes apart and every
-  // access touches 32 lines (config 4 at 33 live qubits: 38 - 50 ms instead of 23 ms per pass).
-  int low_axes = 0;
-  for (int a = 0; a < A; ++a) low_axes += (bt.axbit[a] < 6) ? 1 : 0;
-  const bool want_io = (io_mode == 2) || (io_mode == 1 && low_axes >= 3);
+  // Direct lanes run over the lowest NON-axis bits.  While bit 0, 1 or 2 is one of them a warp access still falls into
+  // runs of >= 32 bytes in a few lines (measured: axes {0, 1} at 27 qubits no loss; axes {2, 3, 4} at 33 live qubits 23.5 ms
+  // direct against 29.0 ms with the two extra transposes); when bits 0 - 2 are all axes the lanes are >= 128 bytes apart
+  // and every access touches 32 lines (config 4 at 33 live qubits: 38 - 50 ms instead of 23 ms per pass).
+  int lowest_dense = 64;
+  for (int k = 0; k < np; ++k) {
+    bool axis = false;
+    for (int a = 0; a < A; ++a) axis = axis || (bt.axbit[a] == pos[k]);
+    if (!axis) { lowest_dense = pos[k]; break; }
+  }
+  const bool want_io = (io_mode == 2) || (io_mode == 1 && lowest_dense >= 3);
   auto same_regs = [&](const Layout& x, const Layout& y) {
     for (int k = 0; k < R; ++k) {
       bool in = false;
@@ -385,19 +390,18 @@ int plan_phases(const Batch& bt, TileBatch* out, int R, uint64_t live_mask = 0, 
       for (int m = 0; m < R; ++m) isreg = isreg || (L.reg[m] == pos[k]);
       if (!isreg) rest[nr++] = pos[k];
     }
+    // three lane bits with distinct canonical index mod 3 (distinct bank groups after the fold) go first, the rest
+    // ascending.  A layout that the tile is loaded / stored in picks them among its five lowest bits: which addresses
+    // a warp covers depends on the SET of its five lane bits only, not on their order.
     int nt = 0;
-    if (!ascending) {
-      // three lane bits with distinct canonical index mod 3 (distinct bank groups after the fold), lowest first
-      bool used_res[3] = {false, false, false};
-      bool taken[16] = {false};
-      for (int k = 0; k < nr && nt < 3; ++k) {
-        const int c = canon(rest[k]) % 3;
-        if (!used_res[c]) { used_res[c] = true; taken[k] = true; L.thr[nt++] = rest[k]; }
-      }
-      for (int k = 0; k < nr; ++k) if (!taken[k]) L.thr[nt++] = rest[k];
-    } else {
-      for (int k = 0; k < nr; ++k) L.thr[nt++] = rest[k];
+    const int window = ascending ? std::min(nr, 5) : nr;
+    bool used_res[3] = {false, false, false};
+    bool taken[16] = {false};
+    for (int k = 0; k < window && nt < 3; ++k) {
+      const int c = canon(rest[k]) % 3;
+      if (!used_res[c]) { used_res[c] = true; taken[k] = true; L.thr[nt++] = rest[k]; }
     }
+    for (int k = 0; k < nr; ++k) if (!taken[k]) L.thr[nt++] = rest[k];
     return L;
   };
   for (int p = 0; p < nph; ++p) {

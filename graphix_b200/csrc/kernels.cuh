@@ -576,8 +576,8 @@ __global__ void __launch_bounds__(TPB, 4) k_fused_batch(double2* __restrict__ ps
 //   phase  = a layout + the consecutive stages whose axes are register bits in it.  Between two layouts the group
 //            transposes through its shared tile (only the group synchronises: __syncwarp, or a named barrier over
 //            32 TW threads — groups and CTAs stay independent, so the FP64 work of one overlaps the loads of others).
-//   I/O    = the first layout is the one the tile is LOADED in, the last one the one it is STORED in.  When three or
-//            more batch axes sit on the lowest physical bits (QFT patterns: 4 - 6 of the axes of a pass on bits 0 - 5)
+//   I/O    = the first layout is the one the tile is LOADED in, the last one the one it is STORED in.  When the three
+//            lowest tile bits are all batch axes (QFT patterns: 4 - 6 of the axes of a pass on physical bits 0 - 5)
 //            the lanes of a direct layout would be >= 128 bytes apart; the host then puts an extra stage-less layout in
 //            front and at the end whose thread bits are the LOWEST bits of the tile — axes or not — so that every
 //            warp-wide access is one contiguous 512-byte run; otherwise the lanes run over the dense bits of the first /

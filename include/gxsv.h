@@ -65,8 +65,8 @@ enum {
   GXSV_OPT_DIST_QUEUE = 10,/* sharded STRICT mode: 1 = projections whose outcome probability is analytic are queued like in
                             * the single-GPU strict mode (gxsv_project_qubit then returns NaN norms and the caller collects
                             * them later with gxsv_take_norms); everything else still returns its local half-norms at once */
-  GXSV_OPT_TILE_IO = 11,   /* tuning: load / store layouts of the multi-axis batched pass: 1 (default) = when three or more batch axes
-                            * lie below physical bit 6 the tile is loaded and stored with the lanes on its LOWEST bits (contiguous
+  GXSV_OPT_TILE_IO = 11,   /* tuning: load / store layouts of the multi-axis batched pass: 1 (default) = when the three lowest bits
+                            * of a tile are all batch axes the tile is loaded and stored with the lanes on its LOWEST bits (contiguous
                             * 512-byte runs) and transposed to / from the first / last phase in shared memory; 0 = never
                             * (lanes on the dense bits of the first / last phase), 2 = always */
   GXSV_OPT_TILE_WARPS = 13,/* tuning: warps that share one tile of the multi-axis batched pass: 0 (default) = by the number

@@ -144,8 +144,8 @@ def test_layout_tables_are_consistent(R, TW, io):
                 assert int(pl["gbits"][p, 1 << la]) == 1 << axis_bits[stage_axis[k]]
             s = s_end[p]
         # I/O layouts: lanes over the lowest tile bits
-        low_axes = sum(1 for b in axis_bits if b < 6)
-        if io == 2 or (io == 1 and low_axes >= 3):
+        lowest_dense = min(b for b in bits if b not in axis_bits)
+        if io == 2 or (io == 1 and lowest_dense >= 3):
             for p in (0, nl - 1):
                 assert [int(x) for x in pl["gtid"][p, :NTB]] == [1 << b for b in bits[:NTB]]
     assert done >= 20
@@ -158,6 +158,8 @@ def test_plain_shape_needs_no_extra_layouts():
     pl = plan(axis_bits, list(range(7)), (1 << 33) - 1, 4, 11, 1)
     assert pl["nph"] == 2 and pl["nl"] == 2
     assert [int(x) for x in pl["gtid"][0, :4]] == [1, 2, 4, 8]
-    pl2 = plan([0, 9, 13, 25, 17, 3, 1], list(range(7)), (1 << 33) - 1, 4, 11, 1)      # three axes on low bits
+    pl2 = plan([0, 9, 13, 25, 17, 2, 1], list(range(7)), (1 << 33) - 1, 4, 11, 1)      # bits 0 - 2 are all axes
     assert pl2["nph"] == 2 and pl2["nl"] == 4
     assert [int(x) for x in pl2["gtid"][0, :7]] == [1, 2, 4, 8, 16, 32, 64]
+    pl3 = plan([2, 15, 28, 3, 16, 29, 4], list(range(7)), (1 << 33) - 1, 4, 11, 1)     # low axes, but bits 0 / 1 are dense
+    assert pl3["nph"] == 2 and pl3["nl"] == 2
