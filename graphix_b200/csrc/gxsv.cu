@@ -436,11 +436,13 @@ int plan_phases(const Batch& bt, TileBatch* out, int R, uint64_t live_mask = 0, 
       for (int k = 0; k < R; ++k)
         if ((b >> k) & 1) { go |= 1ull << lay[p].reg[k]; so |= 1u << canon(lay[p].reg[k]); }
       out->gbits[p][b] = go;
-      out->sbits[p][b] = (unsigned short)sw(so);
+      out->sbits[p][b] = sw(so) * (unsigned int)sizeof(double2);
     }
+    if (p == 0) for (int b = 0; b < 16; ++b) out->gload[b] = out->gbits[0][b] * sizeof(double2);
+    if (p == nl - 1) for (int b = 0; b < 16; ++b) out->gstore[b] = out->gbits[p][b] * sizeof(double2);
     for (int k = 0; k < MAX_THREAD_BITS; ++k) {
       out->gtid[p][k] = (k < NTB) ? (1ull << lay[p].thr[k]) : 0ull;
-      out->stid[p][k] = (k < NTB) ? (unsigned short)sw(1u << canon(lay[p].thr[k])) : (unsigned short)0;
+      out->stid[p][k] = (k < NTB) ? sw(1u << canon(lay[p].thr[k])) * (unsigned int)sizeof(double2) : 0u;
     }
   }
   return nph;
@@ -2216,8 +2218,14 @@ int gxsv_plan_tile_layouts(int naxes, const unsigned char* axis_bits, int nstage
   *nlayouts = tb.nlayouts;
   for (int p = 0; p < MAX_LAYOUTS; ++p) {
     s_end[p] = tb.s_end[p];
-    for (int b = 0; b < 16; ++b) { gbits[p * 16 + b] = tb.gbits[p][b]; sbits[p * 16 + b] = tb.sbits[p][b]; }
-    for (int k = 0; k < MAX_THREAD_BITS; ++k) { gtid[p * MAX_THREAD_BITS + k] = tb.gtid[p][k]; stid[p * MAX_THREAD_BITS + k] = tb.stid[p][k]; }
+    for (int b = 0; b < 16; ++b) {
+      gbits[p * 16 + b] = tb.gbits[p][b];
+      sbits[p * 16 + b] = (unsigned short)(tb.sbits[p][b] / sizeof(double2));     // the kernel's tables hold byte offsets
+    }
+    for (int k = 0; k < MAX_THREAD_BITS; ++k) {
+      gtid[p * MAX_THREAD_BITS + k] = tb.gtid[p][k];
+      stid[p * MAX_THREAD_BITS + k] = (unsigned short)(tb.stid[p][k] / sizeof(double2));
+    }
   }
   for (int k = 0; k < nstages; ++k) lax[k] = tb.lax[k];
   return nph;

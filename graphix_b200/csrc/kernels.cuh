@@ -605,10 +605,11 @@ struct TileBatch {
   unsigned char s_end[MAX_LAYOUTS + 2];       // stages [s_end[p-1], s_end[p]) run in layout p
   unsigned char code[MAX_STAGES + 4];         // 32 * lax + 16 * (accumulate the norm) + variant (SV_*), see stage_by_variant
   StageHot hot[MAX_STAGES + 1];               // the operands of the common variants, packed (one spare entry: fetched ahead)
+  unsigned long long gload[16], gstore[16];              // BYTE offsets of register slot b in the first / last layout
   unsigned long long gbits[MAX_LAYOUTS][16];             // physical offset of register slot b in layout p
   unsigned long long gtid[MAX_LAYOUTS][MAX_THREAD_BITS]; // physical offset contributed by bit i of the thread's index in its group
-  unsigned short sbits[MAX_LAYOUTS][16];                 // the same two as (swizzled) slot offsets inside the group's shared tile
-  unsigned short stid[MAX_LAYOUTS][MAX_THREAD_BITS];
+  unsigned int sbits[MAX_LAYOUTS][16];                   // the same two as (swizzled) BYTE offsets inside the group's shared tile
+  unsigned int stid[MAX_LAYOUTS][MAX_THREAD_BITS];
   double nscale[MAX_STAGES];
   Stage st[MAX_STAGES];
 };
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
   __shared__ unsigned int scode[MAX_STAGES + 4];
   const int F = bt.F;
   const int tid = threadIdx.x, tg = tid & (GT - 1), grp = tid / GT;
-  double2* tile = tile_all + ((size_t)grp << WT);
+  char* tile = reinterpret_cast<char*>(tile_all + ((size_t)grp << WT));   // addressed by XORs of tabulated byte offsets
   auto group_sync = [&]() {
     if (TW == 1) __syncwarp();
     else if (NG == 1) __syncthreads();
@@ -708,10 +709,14 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
     uint64_t gthread = base | gfirst;               // physical index of this thread's amplitudes with the register bits 0
     unsigned int sthread = sfirst;                  // its slot in the group's shared tile, register bits 0
     {
-      const double2* src = psi + gthread;
+      // byte pointer + tabulated byte offsets, the pointer hidden from the optimiser: otherwise every address is
+      // re-derived as psi + 16 (gthread + offset), four 32-bit instructions instead of two
+      const char* src = reinterpret_cast<const char*>(psi + gthread);
+      asm volatile("" : "+l"(src));
 #pragma unroll
       for (int b = 0; b < D; ++b) {
-        const double2 a = src[bt.gbits[0][b]];      // L1-allocating: measured 1 - 2 % faster than ld.global.cs here
+        double2 a;     // explicit ld.global (the hidden pointer would be a generic LD otherwise); L1-allocating: 1 - 2 % faster than .cs
+        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "l"(src + bt.gload[b]));
         v[b] = make_double2(g * a.x, g * a.y);      // the pending normalisation, once per pass
       }
     }
@@ -751,14 +756,15 @@ __global__ void __launch_bounds__(TPB, (R == 3) ? 4 : 2) k_fused_tile(double2* _
         const unsigned int s_new = sthread;
         group_sync();                             // every thread has read its slots of the previous transpose
 #pragma unroll
-        for (int b = 0; b < D; ++b) tile[s_old ^ bt.sbits[p][b]] = v[b];
+        for (int b = 0; b < D; ++b) *reinterpret_cast<double2*>(tile + (s_old ^ bt.sbits[p][b])) = v[b];
         group_sync();
 #pragma unroll
-        for (int b = 0; b < D; ++b) v[b] = tile[s_new ^ bt.sbits[p + 1][b]];
+        for (int b = 0; b < D; ++b) v[b] = *reinterpret_cast<const double2*>(tile + (s_new ^ bt.sbits[p + 1][b]));
       } else {
-        double2* dst = psi + gthread;
+        char* dst = reinterpret_cast<char*>(psi + gthread);
+        asm volatile("" : "+l"(dst));
 #pragma unroll
-        for (int b = 0; b < D; ++b) st_amp(dst + bt.gbits[p][b], v[b]);
+        for (int b = 0; b < D; ++b) st_amp(reinterpret_cast<double2*>(dst + bt.gstore[b]), v[b]);
       }
     }
   }
