@@ -395,8 +395,8 @@ constexpr int MAX_STAGES = 12;
 // kind 2 (general): the four products are in m00..m11 and the stage costs two complex 2-term dot products.
 // kind 0 / 1 (s1 = +-s0, every |+> / |-> partner): the scalar f = s0 c0 (kind 0, |c0| >= |c1|) or f = s0 c1 (kind 1) is
 //   taken out of the stage — the host keeps its phase, the published norms are multiplied by |f|^2 (Batch::nscale) — so that
-//   r0 = t0 + a t1, r1 = +-sv (t0 - a t1), a = c1/c0      (kind 0)       one complex multiply, four additions
-//   r0 = a t0 + t1, r1 = +-sv (a t0 - t1), a = c0/c1      (kind 1)       (12 FP64 operations per pair instead of 21).
+//   r0 = t0 + a t1, r1 = +-sv (t0 - a t1), a = c1/c0      (kind 0)       six fused multiply-adds per pair
+//   r0 = a t0 + t1, r1 = +-sv (a t0 - t1), a = c0/c1      (kind 1)       (stage_pairs; the general form costs 21 operations).
 // The CZ signs are sign-bit XORs: the parity of the thread's fixed index bits is taken once per stage and combined with
 // a host-made table (qtab / vtab: parity contributed by the register-axis bits of the k-th pair, one byte per pair,
 // flag in the byte's top bit so that one byte permute yields the 0 / 0x80000000 mask of a pair).
