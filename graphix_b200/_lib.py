@@ -78,6 +78,7 @@ SIGNATURES = {
     "gxsv_ipc_close": (C.c_int, [_H]),
     "gxsv_swap_peer": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]),
     "gxsv_flush_batch": (C.c_int, [_H]),
+    "gxsv_debug_stage": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _D, _D, _D, C.c_uint64, C.c_uint64, _D]),
     "gxsv_plan_tile_layouts": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, _I,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gxsv_pack_half": (C.c_int, [_H, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),

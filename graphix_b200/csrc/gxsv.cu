@@ -2198,6 +2198,53 @@ int gxsv_ipc_close(gxsv_t* h) {
   return GXSV_OK;
 }
 
+// Host replay of the batched-stage arithmetic (stage_pairs) for CPU tests: v = 2^reg_bits complex amplitudes (re, im
+// interleaved), updated in place.
+extern "C++" {
+template <int NB, int AX>
+static int debug_stage_axis(double2 (&v)[1 << NB], int kind, int acc, int hasv, int uniq, const Stage& st,
+                            unsigned long long tq, unsigned long long tv, double& n0, double& n1) {
+  if (kind == 0 && uniq && !acc && !hasv) stage_pairs<NB, AX, 0, false, false, true>(v, st, st.a, tq, 0ull, n0, n1);
+  else if (kind == 0 && !acc && !hasv) stage_pairs<NB, AX, 0, false, false>(v, st, st.a, tq, 0ull, n0, n1);
+  else if (kind == 0 && acc && !hasv) stage_pairs<NB, AX, 0, true, false>(v, st, st.a, tq, 0ull, n0, n1);
+  else if (kind == 0 && acc && hasv) stage_pairs<NB, AX, 0, true, true>(v, st, st.a, tq, tv, n0, n1);
+  else if (kind == 1 && acc && hasv) stage_pairs<NB, AX, 1, true, true>(v, st, st.a, tq, tv, n0, n1);
+  else if (kind == 2 && acc && hasv) stage_pairs<NB, AX, 2, true, true>(v, st, st.a, tq, tv, n0, n1);
+  else return -1;      // not a variant the kernels instantiate
+  return 0;
+}
+}  // extern "C++"
+
+int gxsv_debug_stage(int reg_bits, int axis, int kind, int acc, int hasv, int uniq, double* amps, const double a[2],
+                     const double m[8], unsigned long long tq, unsigned long long tv, double norm2[1]) {
+  if ((reg_bits != 3 && reg_bits != 4) || axis < 0 || axis >= reg_bits) return -1;
+  Stage st;
+  memset(&st, 0, sizeof st);
+  st.a = make_double2(a[0], a[1]);
+  st.m00 = make_double2(m[0], m[1]); st.m01 = make_double2(m[2], m[3]);
+  st.m10 = make_double2(m[4], m[5]); st.m11 = make_double2(m[6], m[7]);
+  double n0 = 0.0, n1 = 0.0;
+  int rc = -1;
+  if (reg_bits == 4) {
+    double2 v[16];
+    for (int b = 0; b < 16; ++b) v[b] = make_double2(amps[2 * b], amps[2 * b + 1]);
+    if (axis == 0) rc = debug_stage_axis<4, 0>(v, kind, acc, hasv, uniq, st, tq, tv, n0, n1);
+    else if (axis == 1) rc = debug_stage_axis<4, 1>(v, kind, acc, hasv, uniq, st, tq, tv, n0, n1);
+    else if (axis == 2) rc = debug_stage_axis<4, 2>(v, kind, acc, hasv, uniq, st, tq, tv, n0, n1);
+    else rc = debug_stage_axis<4, 3>(v, kind, acc, hasv, uniq, st, tq, tv, n0, n1);
+    for (int b = 0; b < 16; ++b) { amps[2 * b] = v[b].x; amps[2 * b + 1] = v[b].y; }
+  } else {
+    double2 v[8];
+    for (int b = 0; b < 8; ++b) v[b] = make_double2(amps[2 * b], amps[2 * b + 1]);
+    if (axis == 0) rc = debug_stage_axis<3, 0>(v, kind, acc, hasv, uniq, st, tq, tv, n0, n1);
+    else if (axis == 1) rc = debug_stage_axis<3, 1>(v, kind, acc, hasv, uniq, st, tq, tv, n0, n1);
+    else rc = debug_stage_axis<3, 2>(v, kind, acc, hasv, uniq, st, tq, tv, n0, n1);
+    for (int b = 0; b < 8; ++b) { amps[2 * b] = v[b].x; amps[2 * b + 1] = v[b].y; }
+  }
+  norm2[0] = n0 + n1;
+  return rc;
+}
+
 int gxsv_plan_tile_layouts(int naxes, const unsigned char* axis_bits, int nstages, const unsigned char* stage_axis,
                            unsigned long long live_mask, int reg_bits, int tile_log2, int io_mode, int* nlayouts,
                            unsigned char* s_end, unsigned char* lax, unsigned long long* gbits, unsigned long long* gtid,

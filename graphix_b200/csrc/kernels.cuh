@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace gxk {
 
@@ -54,7 +55,7 @@ __device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
   return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
 // a*x + b*y
-__device__ __forceinline__ double2 cmad2(const double2 a, const double2 x, const double2 b, const double2 y) {
+__host__ __device__ __forceinline__ double2 cmad2(const double2 a, const double2 x, const double2 b, const double2 y) {
   double re = a.x * x.x;
   re = fma(-a.y, x.y, re);
   re = fma(b.x, y.x, re);
@@ -420,8 +421,28 @@ struct Batch {
   Stage st[MAX_STAGES];
 };
 
-__device__ __forceinline__ double flip_sign(const double x, const unsigned int s31) {   // s31 = 0 or 0x80000000
+// (the stage arithmetic below is __host__ __device__ so that gxsv_debug_stage can run it on the CPU for tests/test_stage_math.py;
+// the device code is unchanged by that)
+__host__ __device__ __forceinline__ double flip_sign(const double x, const unsigned int s31) {   // s31 = 0 or 0x80000000
+#ifdef __CUDA_ARCH__
   return __hiloint2double(__double2hiint(x) ^ (int)s31, __double2loint(x));
+#else
+  unsigned long long u;
+  memcpy(&u, &x, sizeof u);
+  u ^= (unsigned long long)s31 << 32;
+  double r;
+  memcpy(&r, &u, sizeof r);
+  return r;
+#endif
+}
+// one byte of a sign table -> 0 / 0x80000000 (device: a single byte permute; sel = 0x0444 | (k << 12) moves byte k of t to
+// the top byte and clears the rest)
+__host__ __device__ __forceinline__ unsigned int sign_of_byte(const unsigned int t, const int k) {
+#ifdef __CUDA_ARCH__
+  return __byte_perm(t, 0u, 0x0444 | (k << 12));
+#else
+  return ((t >> (8 * k)) & 0xffu) << 24;
+#endif
 }
 
 // The 2^(NB-1) amplitude pairs of one stage on register axis AX.  KIND as in Stage; ACC = accumulate the norm^2 of
@@ -437,10 +458,10 @@ __device__ __forceinline__ double flip_sign(const double x, const unsigned int s
 // UNIQ (kind 0 only): no CZ partner of the measured qubit sits on another register axis, so the sign of t1 is the same
 // for all pairs of the thread and is folded into the multiplier once (no per-pair sign work at all: 6 DFMA per pair).
 template <int NB, int AX, int KIND, bool ACC, bool HASV, bool UNIQ = false>
-__device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& st, double2 a, const unsigned long long tq64,
+__host__ __device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& st, double2 a, const unsigned long long tq64,
                                             const unsigned long long tv64, double& nrm0, double& nrm1) {
   if (UNIQ) {
-    const unsigned int s = __byte_perm((unsigned int)tq64, 0u, 0x0444);
+    const unsigned int s = sign_of_byte((unsigned int)tq64, 0);
     a.x = flip_sign(a.x, s);
     a.y = flip_sign(a.y, s);
   }
@@ -450,11 +471,11 @@ __device__ __forceinline__ void stage_pairs(double2 (&v)[1 << NB], const Stage& 
     const int hi = lo | (1 << AX);
     const int k = ((lo >> (AX + 1)) << AX) | (lo & ((1 << AX) - 1));   // index of this pair (folded at compile time)
     const unsigned int tq = (k < 4) ? (unsigned int)tq64 : (unsigned int)(tq64 >> 32);
-    const unsigned int sq = UNIQ ? 0u : __byte_perm(tq, 0u, 0x0444 | ((k & 3) << 12));
+    const unsigned int sq = UNIQ ? 0u : sign_of_byte(tq, k & 3);
     unsigned int sv = 0u;
     if (HASV) {
       const unsigned int tv = (k < 4) ? (unsigned int)tv64 : (unsigned int)(tv64 >> 32);
-      sv = __byte_perm(tv, 0u, 0x0444 | ((k & 3) << 12));
+      sv = sign_of_byte(tv, k & 3);
     }
     const double t1x = UNIQ ? v[hi].x : flip_sign(v[hi].x, sq), t1y = UNIQ ? v[hi].y : flip_sign(v[hi].y, sq);
     // order chosen so that every result can take the registers of the operand it replaces (two temporaries per pair):

@@ -214,6 +214,15 @@ int gxsv_ipc_export(gxsv_t* h, unsigned char handle_out[64]);
 int gxsv_ipc_open(gxsv_t* h, int slot, const unsigned char handle[64]);
 int gxsv_ipc_close(gxsv_t* h);
 int gxsv_swap_peer(gxsv_t* h, int q, int slot, int my_bit, double fre, double fim);
+/* Host replay of ONE batched stage (the arithmetic of k_fused_batch / k_fused_tile, compiled for the CPU from the same source)
+ * on the 2^reg_bits amplitudes a thread holds, for tests without a device (tests/test_stage_math.py): amps = 2^reg_bits complex
+ * numbers (re, im interleaved, updated in place), axis = register axis of the stage, kind / acc / hasv / uniq = the variant
+ * (kernels.cuh: stage_pairs), a = the multiplier of kinds 0 / 1, m = the 2x2 of kind 2 (m00, m01, m10, m11), tq / tv = sign
+ * tables (byte k = 0x80: the k-th pair takes the sign), norm2 = accumulated norm^2 of the results (acc = 1).  Returns -1 for a
+ * variant the kernels do not instantiate. */
+int gxsv_debug_stage(int reg_bits, int axis, int kind, int acc, int hasv, int uniq, double* amps, const double a[2],
+                     const double m[8], unsigned long long tq, unsigned long long tv, double norm2[1]);
+
 /* Host-side planner of the multi-axis batched pass (k_fused_tile), exposed so that its tables can be checked without a
  * device: for a batch of `nstages` fused projections whose k-th stage acts on batch axis stage_axis[k] (physical bit
  * axis_bits[stage_axis[k]]), returns the number of register phases and fills, per layout p < *nlayouts (at most 6):
